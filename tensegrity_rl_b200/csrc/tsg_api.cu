@@ -1,0 +1,352 @@
+// tsg_api.cu -- kernels and the C ABI (include/tsg.h) of libtsg.so.  sm_100a only.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tsg.h"
+#include "tsg_host.h"
+
+using namespace tsg;
+
+#ifndef TSG_WARPS
+#define TSG_WARPS 3  // warps (= envs) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
+#endif
+
+static_assert(STATE_STRIDE == TSG_STATE_STRIDE && INFO_DIM == TSG_INFO_DIM && NDRAW == TSG_NDRAW, "ABI constants");
+static_assert(SO_USED <= STATE_STRIDE, "state record too small");
+static_assert(HEADING_SLOTS == TSG_HEADING_SLOTS, "heading slots");
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
+
+constexpr size_t SMEM_TOTAL = SMEM_MODEL + SMEM_CFG + TSG_WARPS * SMEM_SCRATCH;
+
+// One warp per env.  The model constants are staged once per CTA in shared memory (lane-indexed
+// reads of them would serialise in the constant cache); after that warps never synchronise with
+// each other.
+template <int MODE>
+__global__ void __launch_bounds__(TSG_WARPS * 32) tsg_env_kernel(const DevModel* __restrict__ gm,
+                                                                  const EnvCfg* __restrict__ gc, StepIO io) {
+  extern __shared__ __align__(16) unsigned char tsg_smem[];
+  unsigned char* smem = tsg_smem;
+  {
+    const double* src = reinterpret_cast<const double*>(gm);
+    double* dst = reinterpret_cast<double*>(smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const double*>(gc);
+    dst = reinterpret_cast<double*>(smem + SMEM_MODEL);
+    for (int i = threadIdx.x; i < (int)(sizeof(EnvCfg) / 8); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const DevModel& m = *reinterpret_cast<const DevModel*>(smem);
+  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(smem + SMEM_MODEL);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int e = blockIdx.x * TSG_WARPS + warp;
+  if (e >= io.n_envs) return;
+  EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
+  if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
+  else if (MODE == MODE_RESET) { if (io.mask && !io.mask[e]) return; run_reset(S, m, c, io, e, lane); }
+  else run_forward(S, m, c, io, e, lane);
+}
+
+// record <-> separate arrays (tsg_get_state / tsg_set_state)
+__global__ void tsg_gather_kernel(const double* __restrict__ state, int n, double* qpos, double* qvel, double* act,
+                                  double* warm, double* ctrl) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double* r = state + (size_t)e * STATE_STRIDE;
+  if (qpos) for (int i = 0; i < NQ; i++) qpos[(size_t)e * NQ + i] = r[SO_QPOS + i];
+  if (qvel) for (int i = 0; i < NV; i++) qvel[(size_t)e * NV + i] = r[SO_QVEL + i];
+  if (warm) for (int i = 0; i < NV; i++) warm[(size_t)e * NV + i] = r[SO_WARM + i];
+  if (ctrl) for (int i = 0; i < NACT; i++) ctrl[(size_t)e * NACT + i] = r[SO_CTRL + i];
+  if (act) for (int i = 0; i < NACT; i++) act[(size_t)e * NACT + i] = r[SO_ACT + i];
+}
+__global__ void tsg_scatter_kernel(double* __restrict__ state, int n, const double* qpos, const double* qvel,
+                                   const double* act, const double* warm, const double* ctrl) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double* r = state + (size_t)e * STATE_STRIDE;
+  if (qpos) for (int i = 0; i < NQ; i++) r[SO_QPOS + i] = qpos[(size_t)e * NQ + i];
+  if (qvel) for (int i = 0; i < NV; i++) r[SO_QVEL + i] = qvel[(size_t)e * NV + i];
+  if (warm) for (int i = 0; i < NV; i++) r[SO_WARM + i] = warm[(size_t)e * NV + i];
+  if (ctrl) for (int i = 0; i < NACT; i++) r[SO_CTRL + i] = ctrl[(size_t)e * NACT + i];
+  if (act) for (int i = 0; i < NACT; i++) r[SO_ACT + i] = act[(size_t)e * NACT + i];
+}
+__global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const DevModel* m) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double* r = state + (size_t)e * STATE_STRIDE;
+  for (int i = 0; i < STATE_STRIDE; i++) r[i] = 0;
+  for (int i = 0; i < NQ; i++) r[SO_QPOS + i] = m->qpos0[i];
+}
+
+// ------------------------------------------------------------------ handle
+struct TsgHandle {
+  int device, n_envs, obs_dim, launches;
+  long long env_id_base;
+  DevModel* d_model; EnvCfg* d_cfg; float* d_hdata;
+  double* d_state; double* d_heading; double* d_draws;
+  uint8_t* d_done;
+  // staging for the host-buffer entry points
+  double *d_ctrl, *d_obs, *d_reward, *d_info, *d_termobs, *d_tmp;
+  uint8_t* d_mask;
+  cudaStream_t own_stream;
+};
+
+static thread_local std::string g_err;
+const char* tsg_last_error(void) { return g_err.c_str(); }
+int tsg_version(void) { return 1; }
+int tsg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+#define CK(call)                                                                    \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+#define FAIL(msg) do { g_err = (msg); return -1; } while (0)
+
+template <int MODE>
+static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
+  static bool attr_done[3] = {false, false, false};
+  if (!attr_done[MODE]) {
+    CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    attr_done[MODE] = true;
+  }
+  int grid = (h->n_envs + TSG_WARPS - 1) / TSG_WARPS;
+  tsg_env_kernel<MODE><<<grid, TSG_WARPS * 32, SMEM_TOTAL, s>>>(h->d_model, h->d_cfg, io);
+  CK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int device, long long env_id_base,
+               TsgHandle** out) {
+  if (!model || !cfg || !out) FAIL("tsg_create: null argument");
+  if (n_envs < 1) FAIL("tsg_create: n_envs must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); FAIL("tsg_create: no CUDA device (libtsg has no CPU path)"); }
+  if (device < 0 || device >= ndev) FAIL("tsg_create: bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) FAIL("tsg_create: libtsg is built for sm_100a (B200) only");
+  TsgHandle* h = new TsgHandle();
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->n_envs = n_envs; h->env_id_base = env_id_base;
+  if (model->floor_type == TSG_FLOOR_HFIELD) {
+    if (!model->hf_data) { delete h; FAIL("tsg_create: height field data missing"); }
+    size_t nb = (size_t)model->hf_nrow * model->hf_ncol * sizeof(float);
+    CK(cudaMalloc(&h->d_hdata, nb));
+    CK(cudaMemcpy(h->d_hdata, model->hf_data, nb, cudaMemcpyHostToDevice));
+  }
+  DevModel dm; EnvCfg ec;
+  std::string err = make_dev_model(*model, dm, h->d_hdata);
+  if (err.empty()) err = make_env_cfg(*cfg, *model, ec);
+  if (!err.empty()) { tsg_destroy(h); FAIL("tsg_create: " + err); }
+  h->obs_dim = ec.obs_dim;
+  size_t n = (size_t)n_envs;
+  CK(cudaMalloc(&h->d_model, sizeof(DevModel)));
+  CK(cudaMalloc(&h->d_cfg, sizeof(EnvCfg)));
+  CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_cfg, &ec, sizeof(ec), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_state, n * STATE_STRIDE * sizeof(double)));
+  CK(cudaMalloc(&h->d_heading, n * HEADING_SLOTS * sizeof(double)));
+  CK(cudaMalloc(&h->d_draws, n * NDRAW * sizeof(double)));
+  CK(cudaMalloc(&h->d_done, n));
+  CK(cudaMemset(h->d_heading, 0, n * HEADING_SLOTS * sizeof(double)));
+  CK(cudaMemset(h->d_draws, 0, n * NDRAW * sizeof(double)));
+  CK(cudaMemset(h->d_done, 0, n));
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  tsg_init_records_kernel<<<(n_envs + 127) / 128, 128>>>(h->d_state, n_envs, h->d_model);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+int tsg_destroy(TsgHandle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+int tsg_num_envs(const TsgHandle* h) { return h ? h->n_envs : -1; }
+int tsg_obs_dim(const TsgHandle* h) { return h ? h->obs_dim : -1; }
+int tsg_launches(const TsgHandle* h) { return h ? h->launches : -1; }
+int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes, int* regs_per_thread) {
+  (void)h;
+  if (warps_per_cta) *warps_per_cta = TSG_WARPS;
+  if (smem_bytes) *smem_bytes = (int)SMEM_TOTAL;
+  if (regs_per_thread) {
+    cudaFuncAttributes a;
+    CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP>));
+    *regs_per_thread = a.numRegs;
+  }
+  return 0;
+}
+
+static StepIO base_io(TsgHandle* h) {
+  StepIO io;
+  memset(&io, 0, sizeof(io));
+  io.state = h->d_state; io.heading = h->d_heading; io.draws = h->d_draws;
+  io.n_envs = h->n_envs; io.env_id_base = h->env_id_base;
+  return io;
+}
+
+int tsg_reset(TsgHandle* h, const uint8_t* mask_dev, unsigned long long seed, const double* draws_in_dev,
+              double* obs_dev, float* obs32_dev, double* term_obs_dev, void* stream) {
+  if (!h) FAIL("tsg_reset: null handle");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  StepIO io = base_io(h);
+  io.mask = mask_dev; io.seed = seed; io.obs = obs_dev; io.obs32 = obs32_dev; io.term_obs = term_obs_dev;
+  if (draws_in_dev) {
+    CK(cudaMemcpyAsync(h->d_draws, draws_in_dev, (size_t)h->n_envs * NDRAW * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    io.explicit_draws = 1;
+  }
+  return launch_env<MODE_RESET>(h, io, s);
+}
+
+int tsg_step(TsgHandle* h, const void* ctrl_dev, int ctrl_dtype, double* obs_dev, float* obs32_dev, double* reward_dev,
+             uint8_t* done_dev, double* info_dev, int auto_reset, unsigned long long seed, double* term_obs_dev,
+             void* stream) {
+  if (!h) FAIL("tsg_step: null handle");
+  if (!ctrl_dev) FAIL("tsg_step: ctrl_dev is null");
+  if (ctrl_dtype != TSG_CTRL_F64 && ctrl_dtype != TSG_CTRL_F32) FAIL("tsg_step: bad ctrl_dtype");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  StepIO io = base_io(h);
+  if (ctrl_dtype == TSG_CTRL_F64) io.ctrl64 = (const double*)ctrl_dev; else io.ctrl32 = (const float*)ctrl_dev;
+  io.obs = obs_dev; io.obs32 = obs32_dev; io.reward = reward_dev; io.info = info_dev;
+  io.done = done_dev ? done_dev : h->d_done;
+  int rc = launch_env<MODE_STEP>(h, io, s);
+  if (rc) return rc;
+  if (auto_reset) {
+    StepIO r = base_io(h);
+    r.mask = io.done; r.seed = seed; r.obs = obs_dev; r.obs32 = obs32_dev; r.term_obs = term_obs_dev;
+    rc = launch_env<MODE_RESET>(h, r, s);
+  }
+  return rc;
+}
+
+int tsg_forward(TsgHandle* h, double* obs_dev, double* info_dev, void* stream) {
+  if (!h) FAIL("tsg_forward: null handle");
+  CK(cudaSetDevice(h->device));
+  StepIO io = base_io(h);
+  io.obs = obs_dev; io.info = info_dev;
+  return launch_env<MODE_FORWARD>(h, io, (cudaStream_t)stream);
+}
+
+// ---- host-buffer helpers
+static int ensure(double** p, size_t count) {
+  if (*p) return 0;
+  CK(cudaMalloc(p, count * sizeof(double)));
+  return 0;
+}
+int tsg_get_state_host(TsgHandle* h, double* qpos, double* qvel, double* act, double* warm, double* ctrl) {
+  if (!h) FAIL("tsg_get_state_host: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t n = h->n_envs;
+  if (ensure(&h->d_tmp, n * (NQ + 2 * NV + 2 * NACT))) return -2;
+  double *dq = h->d_tmp, *dv = dq + n * NQ, *dw = dv + n * NV, *dc = dw + n * NV, *da = dc + n * NACT;
+  CK(cudaDeviceSynchronize());
+  tsg_gather_kernel<<<(h->n_envs + 127) / 128, 128>>>(h->d_state, h->n_envs, dq, dv, da, dw, dc);
+  CK(cudaGetLastError());
+  if (qpos) CK(cudaMemcpy(qpos, dq, n * NQ * 8, cudaMemcpyDeviceToHost));
+  if (qvel) CK(cudaMemcpy(qvel, dv, n * NV * 8, cudaMemcpyDeviceToHost));
+  if (warm) CK(cudaMemcpy(warm, dw, n * NV * 8, cudaMemcpyDeviceToHost));
+  if (ctrl) CK(cudaMemcpy(ctrl, dc, n * NACT * 8, cudaMemcpyDeviceToHost));
+  if (act) CK(cudaMemcpy(act, da, n * NACT * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int tsg_set_state_host(TsgHandle* h, const double* qpos, const double* qvel, const double* act, const double* warm,
+                       const double* ctrl) {
+  if (!h) FAIL("tsg_set_state_host: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t n = h->n_envs;
+  if (ensure(&h->d_tmp, n * (NQ + 2 * NV + 2 * NACT))) return -2;
+  double *dq = h->d_tmp, *dv = dq + n * NQ, *dw = dv + n * NV, *dc = dw + n * NV, *da = dc + n * NACT;
+  CK(cudaDeviceSynchronize());
+  if (qpos) CK(cudaMemcpy(dq, qpos, n * NQ * 8, cudaMemcpyHostToDevice));
+  if (qvel) CK(cudaMemcpy(dv, qvel, n * NV * 8, cudaMemcpyHostToDevice));
+  if (warm) CK(cudaMemcpy(dw, warm, n * NV * 8, cudaMemcpyHostToDevice));
+  if (ctrl) CK(cudaMemcpy(dc, ctrl, n * NACT * 8, cudaMemcpyHostToDevice));
+  if (act) CK(cudaMemcpy(da, act, n * NACT * 8, cudaMemcpyHostToDevice));
+  tsg_scatter_kernel<<<(h->n_envs + 127) / 128, 128>>>(h->d_state, h->n_envs, qpos ? dq : nullptr, qvel ? dv : nullptr,
+                                                        act ? da : nullptr, warm ? dw : nullptr, ctrl ? dc : nullptr);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+int tsg_get_records_host(TsgHandle* h, double* records) {
+  if (!h || !records) FAIL("tsg_get_records_host: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(records, h->d_state, (size_t)h->n_envs * STATE_STRIDE * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int tsg_set_records_host(TsgHandle* h, const double* records) {
+  if (!h || !records) FAIL("tsg_set_records_host: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h->d_state, records, (size_t)h->n_envs * STATE_STRIDE * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+int tsg_get_draws_host(TsgHandle* h, double* draws) {
+  if (!h || !draws) FAIL("tsg_get_draws_host: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(draws, h->d_draws, (size_t)h->n_envs * NDRAW * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int tsg_step_host(TsgHandle* h, const double* ctrl, double* obs, double* reward, uint8_t* done, double* info,
+                  int auto_reset, unsigned long long seed, double* term_obs) {
+  if (!h || !ctrl) FAIL("tsg_step_host: null argument");
+  CK(cudaSetDevice(h->device));
+  size_t n = h->n_envs, od = h->obs_dim;
+  if (ensure(&h->d_ctrl, n * NACT) || ensure(&h->d_obs, n * od) || ensure(&h->d_reward, n) ||
+      ensure(&h->d_info, n * INFO_DIM) || ensure(&h->d_termobs, n * od)) return -2;
+  cudaStream_t s = h->own_stream;
+  CK(cudaMemcpyAsync(h->d_ctrl, ctrl, n * NACT * 8, cudaMemcpyHostToDevice, s));
+  int rc = tsg_step(h, h->d_ctrl, TSG_CTRL_F64, h->d_obs, nullptr, h->d_reward, h->d_done, info ? h->d_info : nullptr,
+                    auto_reset, seed, term_obs ? h->d_termobs : nullptr, s);
+  if (rc) return rc;
+  if (obs) CK(cudaMemcpyAsync(obs, h->d_obs, n * od * 8, cudaMemcpyDeviceToHost, s));
+  if (reward) CK(cudaMemcpyAsync(reward, h->d_reward, n * 8, cudaMemcpyDeviceToHost, s));
+  if (done) CK(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, s));
+  if (info) CK(cudaMemcpyAsync(info, h->d_info, n * INFO_DIM * 8, cudaMemcpyDeviceToHost, s));
+  if (term_obs) CK(cudaMemcpyAsync(term_obs, h->d_termobs, n * od * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+int tsg_reset_host(TsgHandle* h, const uint8_t* mask, unsigned long long seed, const double* draws_in, double* obs) {
+  if (!h) FAIL("tsg_reset_host: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t n = h->n_envs, od = h->obs_dim;
+  if (ensure(&h->d_obs, n * od)) return -2;
+  cudaStream_t s = h->own_stream;
+  if (mask) {
+    if (!h->d_mask) CK(cudaMalloc(&h->d_mask, n));
+    CK(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s));
+  }
+  double* d_draws_in = nullptr;
+  if (draws_in) {
+    if (ensure(&h->d_tmp, n * (NQ + 2 * NV + 2 * NACT))) return -2;
+    d_draws_in = h->d_tmp;
+    CK(cudaMemcpyAsync(d_draws_in, draws_in, n * NDRAW * 8, cudaMemcpyHostToDevice, s));
+  }
+  int rc = tsg_reset(h, mask ? h->d_mask : nullptr, seed, d_draws_in, h->d_obs, nullptr, nullptr, s);
+  if (rc) return rc;
+  if (obs) CK(cudaMemcpyAsync(obs, h->d_obs, n * od * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}

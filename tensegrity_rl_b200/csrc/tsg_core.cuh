@@ -1,0 +1,1286 @@
+// tsg_core.cuh -- one-warp-per-env tensegrity step for sm_100a.
+//
+// Each warp owns ONE environment for a whole env step: the 18-DoF state, tendon
+// Jacobians, contact rows and the 18x18 Newton Hessian live in that warp's slice
+// of shared memory for all frame_skip substeps; HBM is touched only at the step
+// boundary (one contiguous state record per env, ctrl in, obs/reward/done out).
+// Work inside a substep is spread over the 32 lanes as "items" (tendons, dofs,
+// contact rows, Hessian entries, collision candidates) separated by __syncwarp().
+//
+// What is computed is MuJoCo 2.3.7's mj_step for this model:
+// kinematics -> tendons -> collision (plane / height field / bar-bar with MPR)
+// -> elliptic condim-6 contact rows -> smooth forces -> Newton with exact line
+// search -> implicitfast -> advance; then the tr_env / tensegrity_env epilogue
+// (tr_env.py:327-527, tensegrity_env.py:291-430).
+//
+// The same source compiles as plain C++ with TSG_HOST_EMUL (a serial "one warp"
+// emulator used ONLY by tests/emul to debug the lane logic without a GPU; the
+// product library never builds or calls it).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(TSG_HOST_EMUL)
+#define TSG_DEVICE 1
+#define TSG_FN __device__ __forceinline__
+#define TSG_FN_NOINLINE __device__ __noinline__
+#define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
+#define LANE_FOR_ALL(i, n) for (int i##_b = 0, i = lane; i##_b < (n); i##_b += 32, i += 32)
+#define WSYNC() __syncwarp()
+#else
+#define TSG_DEVICE 0
+#define TSG_FN static inline
+#define TSG_FN_NOINLINE static
+#define LANE_FOR(i, n) for (int i = 0; i < (n); ++i)
+#define LANE_FOR_ALL(i, n) for (int i = 0; i < (n); ++i)
+#define WSYNC() ((void)0)
+#endif
+
+namespace tsg {
+
+constexpr int NBAR = 3, NGEOM = 15, NTEN = 9, NEND = 18, NACT = 6, NQ = 21, NV = 18;
+constexpr int MAXC = 12;        // contact slots per env in shared memory
+constexpr int MAXCAND = 64;     // narrow-phase candidates per collision pass
+constexpr int HS = 19;          // padded row stride of the Hessian
+constexpr double MINVAL = 1e-15, MAXVAL = 1e10, MINIMP = 0.0001, MAXIMP = 0.9999;
+constexpr double CCD_EPS = 2.220446049250313e-16;
+constexpr int GEOM_SPHERE = 2, GEOM_CYL = 5;
+constexpr int ZONE_TOP = 0, ZONE_BOTTOM = 1, ZONE_MIDDLE = 2;
+constexpr int STATE_STRIDE = 96;  // doubles per env record in HBM (768 B, 128 B aligned)
+constexpr int INFO_DIM = 32;
+constexpr int HEADING_SLOTS = 32;
+constexpr int NDRAW = 10;
+
+// offsets into the per-env state record
+enum StateOff {
+  SO_QPOS = 0, SO_QVEL = 21, SO_WARM = 39, SO_CTRL = 57, SO_ACT = 63,
+  SO_XY_PREV = 69, SO_PSI_PREV = 71, SO_RESET_PSI = 72, SO_WAYPT = 73, SO_ORI = 75,
+  SO_STEP_NUM = 77, SO_EP_RET = 78, SO_EP_LEN = 79, SO_XVEL = 80, SO_YVEL = 81,
+  SO_HEAD_N = 82, SO_HEAD_POS = 83, SO_FLAGS = 84, SO_NRESET = 85, SO_USED = 86
+};
+// info row (per env, per step)
+enum InfoOff {
+  IO_REW_FWD = 0, IO_REW_CTRL, IO_REW_SURVIVE, IO_X, IO_Y, IO_PSI, IO_XVEL, IO_YVEL,
+  IO_TEN = 8 /* 9 */, IO_TERMINATED = 17, IO_TRUNCATED, IO_NCON, IO_NITER, IO_NLS, IO_BARFORCE, IO_MAXCFRC,
+  IO_WAYPT = 24 /* 2 */, IO_ORI = 26 /* 2 */, IO_OVERFLOW = 28, IO_BAD = 29, IO_NMPR = 30
+};
+
+struct DevModel {
+  double h, grav[3], tol, ls_tol, mpr_tol, meaninertia;
+  int iterations, ls_iterations, mpr_iterations;
+  unsigned flags;
+  double M[NV], invM[NV];
+  double inertia[NBAR][3];
+  double invw_tran[NBAR];
+  int gtype[NGEOM];
+  int pad0;
+  double gsize[NGEOM][2];
+  double gpos[NGEOM][3];
+  // tendons
+  int tbody[NEND];
+  double tsite[NEND][3];
+  double tk[NTEN], tdamp[NTEN], tls[NTEN][2];
+  int ten_act[NTEN];
+  int nends[NBAR];
+  int ends[NBAR][8];
+  int act_tendon[NACT];
+  int dyntype, ctrllimited, forcelimited, pad1;
+  double dynprm0, gain, bias[3], ctrlrange[2], forcerange[2];
+  // contact
+  double K, B, solimp[5], mu, fr[5], dscale[6], fscale[6];
+  // floor
+  int floor_type, nrow, ncol, pad2;
+  double fpos[3], fnormal[3], hsize[4];
+  const float* hdata;
+  double qpos0[NQ];
+};
+
+struct EnvCfg {
+  int env_kind, task, frame_skip, obs_dim, use_cap_velocity, terminate_when_unhealthy, is_test;
+  int reward_delay_steps, max_episode_steps, warmup_steps, npose, pad;
+  double desired_direction, ctrl_cost_weight, healthy_reward, yaw_reward_weight;
+  double min_reset_heading, max_reset_heading;
+  double tendon_reset_mean, tendon_reset_stdev, tendon_min_length, tendon_max_length;
+  double waypt_range[2], waypt_angle_range[2];
+  double ditch_reward_max, ditch_reward_stdev, waypt_reward_amplitude, waypt_reward_stdev, kill_force, dt;
+  double reset_pose[6][NQ];
+};
+
+struct Con {
+  double J[2][6][6];  // [side][row][dof of that side's bar], sign applied
+  double frame[9];
+  double pos[3];
+  double aref[6], jar[6], jv[6], force[6], w[6];
+  double bvec[2][6];
+  double su[6];
+  double dist, D0, ca, cb;
+  double U0, V0, UU, UV, VV, q0, q1, q2;
+  int b1, b2;  // bar index 0..2, or -1 for the world
+  int zone, active;
+};
+
+struct Scratch {
+  // env state carried across substeps
+  double qpos[NQ], qvel[NV], warm[NV], ctrl[NACT], act[NACT];
+  // position stage
+  double xstale[9];
+  double xmat[27];
+  double site[NEND * 3];
+  double gpos[NGEOM * 3];
+  double tlen[NTEN], tdir[NTEN * 3], tJw[NEND * 3];
+  // velocity / force stage
+  double tvel[NTEN], tfrc[NTEN], tB[NTEN], actfrc[NACT], actdot[NACT];
+  double fsm[NV], asmooth[NV], fcon[NV];
+  double Dblk[NBAR][21];
+  // solver
+  double qacc[NV], grad[NV], search[NV], rhs[NV], dinv[NV];
+  double H[NV * HS];
+  double lsacc[2][MAXC][3];
+  double red[32];
+  double cfrc[4][6];
+  Con con[MAXC];
+  int order[MAXC];
+  int cand[MAXCAND];
+  int hf_cell[NGEOM][4];
+  double hf_zmin[NGEOM];
+  int nact, nslot, overflow, bad;
+  int niter_total, nls_total, nmpr_total, pad;
+};
+
+struct EnvScratch : Scratch {
+  double heading[HEADING_SLOTS];
+  double obs[64];
+  double action[NACT];
+  double draws[NDRAW + 2];
+};
+
+
+// ---- shared-memory context.  Heavy stages are compiled ONCE as __noinline__ functions; on the device
+// they re-derive their context from the dynamic shared-memory base so that the compiler keeps LDS/STS
+// addressing (a reference passed through a call would degrade to generic loads).
+constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+constexpr size_t SMEM_MODEL = align16(sizeof(DevModel));
+constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
+constexpr size_t SMEM_SCRATCH = align16(sizeof(EnvScratch));
+#if TSG_DEVICE
+#define CTX_PARAMS int lane
+#define CTX_ARGS lane
+#define CTX_BIND                                                                                         \
+  extern __shared__ __align__(16) unsigned char tsg_smem[];                                              \
+  EnvScratch& S = *reinterpret_cast<EnvScratch*>(tsg_smem + SMEM_MODEL + SMEM_CFG + (threadIdx.x >> 5) * SMEM_SCRATCH); \
+  const DevModel& m = *reinterpret_cast<const DevModel*>(tsg_smem);                                      \
+  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tsg_smem + SMEM_MODEL);                             \
+  (void)c; (void)m;
+#else
+#define CTX_PARAMS EnvScratch &S, const DevModel &m, const EnvCfg &c, int lane
+#define CTX_ARGS S, m, c, lane
+#define CTX_BIND (void)c;
+#endif
+
+// ------------------------------------------------------------------ small math
+TSG_FN double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+TSG_FN void cross3(double* r, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+TSG_FN void sub3(double* r, const double* a, const double* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+TSG_FN void add3(double* r, const double* a, const double* b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+TSG_FN void copy3(double* r, const double* a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+TSG_FN void scl3(double* r, const double* a, double s) { r[0] = a[0] * s; r[1] = a[1] * s; r[2] = a[2] * s; }
+TSG_FN void addscl3(double* r, const double* a, double s) { r[0] += a[0] * s; r[1] += a[1] * s; r[2] += a[2] * s; }
+TSG_FN double normalize3(double* a) {
+  double n = sqrt(dot3(a, a));
+  if (n < MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; }
+  else { double s = 1 / n; a[0] *= s; a[1] *= s; a[2] *= s; }
+  return n;
+}
+TSG_FN void mulMV(double* r, const double* R, const double* v) {
+  double x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  double y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+TSG_FN void mulMTV(double* r, const double* R, const double* v) {
+  double x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  double y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  double z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+TSG_FN void quat2mat(double* R, const double* q) {
+  double q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  double q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3];
+  double q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  R[0] = q00 + q11 - q22 - q33; R[4] = q00 - q11 + q22 - q33; R[8] = q00 - q11 - q22 + q33;
+  R[1] = 2 * (q12 - q03); R[2] = 2 * (q13 + q02);
+  R[3] = 2 * (q12 + q03); R[5] = 2 * (q23 - q01);
+  R[6] = 2 * (q13 - q02); R[7] = 2 * (q23 + q01);
+}
+TSG_FN void normalize4(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else if (fabs(n - 1) > MINVAL) { double s = 1 / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+}
+TSG_FN bool is_bad(double x) { return !(x <= MAXVAL && x >= -MAXVAL); }
+TSG_FN double clampd(double x, double lo, double hi) { return fmin(hi, fmax(lo, x)); }
+
+// exclusive prefix sum of `v` over the items of one LANE_FOR_ALL pass; `total` is a warp-uniform
+// running count.  Device: shuffle scan.  Host emulator: items arrive serially in order.
+TSG_FN int scan_slot(int v, int& total, int lane) {
+#if TSG_DEVICE
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int slot = total + incl - v;
+  total += __shfl_sync(0xffffffffu, incl, 31);
+  return slot;
+#else
+  (void)lane;
+  int slot = total;
+  total += v;
+  return slot;
+#endif
+}
+
+// ------------------------------------------------------------------ kinematics + tendons
+TSG_FN void stage_position(Scratch& S, const DevModel& m, int lane) {
+  LANE_FOR(b, NBAR) {
+    double* q = S.qpos + 7 * b;
+    normalize4(q + 3);
+    quat2mat(S.xmat + 9 * b, q + 3);
+    copy3(S.xstale + 3 * b, q);
+  }
+  WSYNC();
+  LANE_FOR(i, NEND + NGEOM) {
+    int b; const double* loc; double* out;
+    if (i < NEND) { b = m.tbody[i]; loc = m.tsite[i]; out = S.site + 3 * i; }
+    else { int g = i - NEND; b = g / 5; loc = m.gpos[g]; out = S.gpos + 3 * g; }
+    double v[3];
+    mulMV(v, S.xmat + 9 * b, loc);
+    add3(out, S.qpos + 7 * b, v);
+  }
+  WSYNC();
+}
+
+TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
+  LANE_FOR(t, NTEN) {
+    double dir[3], w[2][3];
+    sub3(dir, S.site + 3 * (2 * t + 1), S.site + 3 * (2 * t));
+    double len = normalize3(dir);
+    double vel = 0;
+    for (int e = 0; e < 2; e++) {
+      int end = 2 * t + e, b = m.tbody[end];
+      double r[3], c[3];
+      sub3(r, S.site + 3 * end, S.qpos + 7 * b);
+      cross3(c, r, dir);
+      mulMTV(w[e], S.xmat + 9 * b, c);
+      copy3(S.tJw + 3 * end, w[e]);
+      double s = e ? 1.0 : -1.0;
+      vel += s * (dot3(dir, S.qvel + 6 * b) + dot3(w[e], S.qvel + 6 * b + 3));
+    }
+    copy3(S.tdir + 3 * t, dir);
+    S.tlen[t] = len; S.tvel[t] = vel;
+    double frc = 0, Bt = -m.tdamp[t];
+    if (m.tk[t] > 0) {
+      if (len > m.tls[t][1]) frc = m.tk[t] * (m.tls[t][1] - len);
+      else if (len < m.tls[t][0]) frc = m.tk[t] * (m.tls[t][0] - len);
+    }
+    frc -= m.tdamp[t] * vel;
+    int a = m.ten_act[t];
+    if (a >= 0) {
+      double ctrl = S.ctrl[a], input;
+      if (m.ctrllimited) ctrl = clampd(ctrl, m.ctrlrange[0], m.ctrlrange[1]);
+      if (m.dyntype) { S.actdot[a] = (ctrl - S.act[a]) / fmax(MINVAL, m.dynprm0); input = S.act[a]; }
+      else { S.actdot[a] = 0; input = ctrl; }
+      double f = m.gain * input + m.bias[0] + m.bias[1] * len + m.bias[2] * vel;
+      bool clamped = false;
+      if (m.forcelimited) {
+        clamped = (f <= m.forcerange[0] || f >= m.forcerange[1]);
+        f = clampd(f, m.forcerange[0], m.forcerange[1]);
+      }
+      S.actfrc[a] = f;
+      frc += f;
+      if (m.bias[2] != 0 && ((m.flags & 1u) || !clamped)) Bt += m.bias[2];
+    }
+    S.tfrc[t] = frc; S.tB[t] = Bt;
+  }
+  WSYNC();
+}
+
+// qfrc_smooth / qacc_smooth (items 0..17) and the per-bar damping-derivative blocks (items 18..80)
+TSG_FN void stage_smooth(Scratch& S, const DevModel& m, int lane) {
+  LANE_FOR(i, NV + 63) {
+    if (i < NV) {
+      int b = i / 6, j = i % 6;
+      double f = 0;
+      for (int n = 0; n < m.nends[b]; n++) {
+        int end = m.ends[b][n], t = end >> 1;
+        double s = (end & 1) ? 1.0 : -1.0;
+        double Jv = j < 3 ? S.tdir[3 * t + j] : S.tJw[3 * end + j - 3];
+        f += s * S.tfrc[t] * Jv;
+      }
+      double bias;
+      if (j < 3) bias = -m.M[i] * m.grav[j];
+      else {
+        const double* w = S.qvel + 6 * b + 3; const double* I = m.inertia[b];
+        int k = j - 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        bias = w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]);
+      }
+      S.fsm[i] = f - bias;
+      S.asmooth[i] = (f - bias) * m.invM[i];
+    } else {
+      int idx = i - NV, b = idx / 21, tri = idx % 21;
+      int r = 0; while ((r + 1) * (r + 2) / 2 <= tri) r++;
+      int c = tri - r * (r + 1) / 2;
+      double v = 0;
+      for (int n = 0; n < m.nends[b]; n++) {
+        int end = m.ends[b][n], t = end >> 1;
+        double Jr = r < 3 ? S.tdir[3 * t + r] : S.tJw[3 * end + r - 3];
+        double Jc = c < 3 ? S.tdir[3 * t + c] : S.tJw[3 * end + c - 3];
+        v += S.tB[t] * Jr * Jc;
+      }
+      S.Dblk[b][tri] = v;
+    }
+  }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------ MPR (libccd semantics)
+struct CObj { int type; double pos[3]; const double* mat; double size[2]; const double* prism; };
+struct Supp { double v[3], v1[3]; };  // v = v1 - v2 ; v2 recovered as v1 - v
+
+TSG_FN bool ccd_is_zero(double x) { return fabs(x) < CCD_EPS; }
+TSG_FN bool ccd_eq(double a_, double b_) {
+  double ab = fabs(a_ - b_);
+  if (ab < CCD_EPS) return true;
+  double a = fabs(a_), b = fabs(b_);
+  return (b > a) ? (ab < CCD_EPS * b) : (ab < CCD_EPS * a);
+}
+TSG_FN bool ccd_vec_is_origin(const double* a) { return ccd_eq(a[0], 0) && ccd_eq(a[1], 0) && ccd_eq(a[2], 0); }
+TSG_FN void ccd_normalize(double* v) { double s = 1.0 / sqrt(dot3(v, v)); v[0] *= s; v[1] *= s; v[2] *= s; }
+
+TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
+  if (o.type == 100) {
+    int best = 0; double bd = dot3(o.prism, dir);
+    for (int i = 1; i < 6; i++) { double dd = dot3(o.prism + 3 * i, dir); if (dd > bd) { bd = dd; best = i; } }
+    copy3(out, o.prism + 3 * best);
+    return;
+  }
+  double ld[3], res[3];
+  mulMTV(ld, o.mat, dir);
+  if (o.type == GEOM_SPHERE) scl3(res, ld, o.size[0]);
+  else {
+    double tmp = sqrt(ld[0] * ld[0] + ld[1] * ld[1]);
+    if (tmp > MINVAL) { res[0] = ld[0] / tmp * o.size[0]; res[1] = ld[1] / tmp * o.size[0]; }
+    else res[0] = res[1] = 0;
+    res[2] = (ld[2] > 0 ? 1.0 : (ld[2] < 0 ? -1.0 : 0.0)) * o.size[1];
+  }
+  mulMV(out, o.mat, res);
+  add3(out, out, o.pos);
+}
+TSG_FN void obj_center(const CObj& o, double* c) {
+  if (o.type == 100) {
+    c[0] = c[1] = c[2] = 0;
+    for (int i = 0; i < 6; i++) { c[0] += o.prism[3 * i]; c[1] += o.prism[3 * i + 1]; c[2] += o.prism[3 * i + 2]; }
+    c[0] /= 6; c[1] /= 6; c[2] /= 6;
+  } else copy3(c, o.pos);
+}
+TSG_FN void mink_support(const CObj& o1, const CObj& o2, const double* dir, Supp& s) {
+  double nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
+  obj_support(o1, dir, s.v1);
+  obj_support(o2, nd, v2);
+  sub3(s.v, s.v1, v2);
+}
+TSG_FN void portal_dir(const Supp* p, double* dir) {
+  double a[3], b[3];
+  sub3(a, p[2].v, p[1].v); sub3(b, p[3].v, p[1].v);
+  cross3(dir, a, b); ccd_normalize(dir);
+}
+TSG_FN bool portal_reach_tol(const Supp* p, const Supp& v4, const double* dir, double tol) {
+  double dv4 = dot3(v4.v, dir);
+  double d1 = dv4 - dot3(p[1].v, dir), d2 = dv4 - dot3(p[2].v, dir), d3 = dv4 - dot3(p[3].v, dir);
+  d1 = fmin(d1, d2); d1 = fmin(d1, d3);
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+TSG_FN void expand_portal(Supp* p, const Supp& v4) {
+  double v4v0[3];
+  cross3(v4v0, v4.v, p[0].v);
+  if (dot3(p[1].v, v4v0) > 0) { if (dot3(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4; }
+  else { if (dot3(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4; }
+}
+TSG_FN double seg_dist2_origin(const double* x0, const double* b, double* wit) {
+  double d[3];
+  sub3(d, b, x0);
+  double t = -1.0 * dot3(x0, d); t /= dot3(d, d);
+  if (t < 0 || ccd_is_zero(t)) copy3(wit, x0);
+  else if (t > 1 || ccd_eq(t, 1.0)) copy3(wit, b);
+  else { scl3(wit, d, t); add3(wit, wit, x0); }
+  return dot3(wit, wit);
+}
+TSG_FN double tri_dist2_origin(const double* x0, const double* B, const double* C, double* wit) {
+  double d1[3], d2[3];
+  sub3(d1, B, x0); sub3(d2, C, x0);
+  double v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  double s, t, dist, dd = w * v - r * r;
+  if (ccd_is_zero(dd)) s = t = -1;
+  else { s = (q * r - w * p) / dd; t = (-s * r - q) / w; }
+  if ((ccd_is_zero(s) || s > 0) && (ccd_eq(s, 1.0) || s < 1) && (ccd_is_zero(t) || t > 0) &&
+      (ccd_eq(t, 1.0) || t < 1) && (ccd_eq(t + s, 1.0) || t + s < 1)) {
+    scl3(d1, d1, s); scl3(d2, d2, t);
+    copy3(wit, x0); add3(wit, wit, d1); add3(wit, wit, d2);
+    dist = dot3(wit, wit);
+  } else {
+    double w2[3], dist2;
+    dist = seg_dist2_origin(x0, B, wit);
+    dist2 = seg_dist2_origin(x0, C, w2);
+    if (dist2 < dist) { dist = dist2; copy3(wit, w2); }
+    dist2 = seg_dist2_origin(B, C, w2);
+    if (dist2 < dist) { dist = dist2; copy3(wit, w2); }
+  }
+  return dist;
+}
+// returns true on penetration; dir points from obj1 to obj2
+TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol, int max_iter,
+                                     double* depth, double* dir_out, double* pos_out) {
+  Supp p[4], v4;
+  double dir[3], va[3], vb[3], dot, c2[3];
+  // ---- discoverPortal
+  obj_center(o1, p[0].v1); obj_center(o2, c2);
+  sub3(p[0].v, p[0].v1, c2);
+  if (ccd_vec_is_origin(p[0].v)) p[0].v[0] += CCD_EPS * 10.0;
+  scl3(dir, p[0].v, -1.0); ccd_normalize(dir);
+  mink_support(o1, o2, dir, p[1]);
+  dot = dot3(p[1].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return false;
+  cross3(dir, p[0].v, p[1].v);
+  if (ccd_is_zero(dot3(dir, dir))) {
+    // origin on v1 (touching: depth 0, no direction -> MuJoCo drops it) or on the v0-v1 segment
+    if (ccd_vec_is_origin(p[1].v)) return false;
+    double v2[3];
+    sub3(v2, p[1].v1, p[1].v);
+    add3(pos_out, p[1].v1, v2); scl3(pos_out, pos_out, 0.5);
+    copy3(dir_out, p[1].v); *depth = sqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
+    return true;
+  }
+  ccd_normalize(dir);
+  mink_support(o1, o2, dir, p[2]);
+  dot = dot3(p[2].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return false;
+  sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
+  cross3(dir, va, vb); ccd_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) { Supp t = p[1]; p[1] = p[2]; p[2] = t; scl3(dir, dir, -1.0); }
+  for (;;) {
+    bool cont = false;
+    mink_support(o1, o2, dir, p[3]);
+    dot = dot3(p[3].v, dir);
+    if (ccd_is_zero(dot) || dot < 0) return false;
+    cross3(va, p[1].v, p[3].v); dot = dot3(va, p[0].v);
+    if (dot < 0 && !ccd_is_zero(dot)) { p[2] = p[3]; cont = true; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v); dot = dot3(va, p[0].v);
+      if (dot < 0 && !ccd_is_zero(dot)) { p[1] = p[3]; cont = true; }
+    }
+    if (!cont) break;
+    sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
+    cross3(dir, va, vb); ccd_normalize(dir);
+  }
+  // ---- refinePortal
+  for (;;) {
+    portal_dir(p, dir);
+    dot = dot3(dir, p[1].v);
+    if (ccd_is_zero(dot) || dot > 0) break;
+    mink_support(o1, o2, dir, v4);
+    dot = dot3(v4.v, dir);
+    if (!(ccd_is_zero(dot) || dot > 0) || portal_reach_tol(p, v4, dir, tol)) return false;
+    expand_portal(p, v4);
+  }
+  // ---- findPenetr
+  for (int it = 0;; it++) {
+    portal_dir(p, dir);
+    mink_support(o1, o2, dir, v4);
+    if (portal_reach_tol(p, v4, dir, tol) || it > max_iter) {
+      double pdir[3];
+      *depth = sqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
+      if (ccd_is_zero(pdir[0]) && ccd_is_zero(pdir[1]) && ccd_is_zero(pdir[2])) copy3(pdir, dir);
+      ccd_normalize(pdir);
+      copy3(dir_out, pdir);
+      // findPos: barycentric blend of the witness points
+      double vec[3], b[4], sum;
+      portal_dir(p, dir);
+      cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
+      cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
+      cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
+      cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
+      sum = b[0] + b[1] + b[2] + b[3];
+      if (ccd_is_zero(sum) || sum < 0) {
+        b[0] = 0;
+        cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
+        cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
+        cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
+        sum = b[1] + b[2] + b[3];
+      }
+      double inv = 1.0 / sum, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+      // v0's second witness is obj2's centre
+      for (int i = 0; i < 4; i++) {
+        double v2[3];
+        if (i == 0) copy3(v2, c2); else sub3(v2, p[i].v1, p[i].v);
+        addscl3(p1, p[i].v1, b[i]); addscl3(p2, v2, b[i]);
+      }
+      scl3(p1, p1, inv); scl3(p2, p2, inv);
+      add3(pos_out, p1, p2); scl3(pos_out, pos_out, 0.5);
+      return true;
+    }
+    expand_portal(p, v4);
+  }
+}
+
+// ------------------------------------------------------------------ collision
+TSG_FN void make_frame(double* f) {
+  normalize3(f);
+  f[3] = f[4] = f[5] = 0;
+  if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
+  double t = dot3(f, f + 3);
+  addscl3(f + 3, f, -t);
+  normalize3(f + 3);
+  cross3(f + 6, f, f + 3);
+}
+TSG_FN void set_contact(Con& c, int b1, int b2, double dist, const double* pos, const double* normal) {
+  c.b1 = b1; c.b2 = b2; c.dist = dist;
+  copy3(c.pos, pos);
+  copy3(c.frame, normal);
+  make_frame(c.frame);
+  c.active = dist < 0 ? 1 : 0;  // includemargin 0: dist >= 0 gives no rows
+}
+// squared distance between segments p1 +- a1, p2 +- a2 (a = half-axis vectors)
+TSG_FN double segseg_dist2(const double* p1, const double* a1, const double* p2, const double* a2) {
+  double r[3]; sub3(r, p1, p2);
+  double A = dot3(a1, a1), E = dot3(a2, a2), Bq = dot3(a1, a2), C = dot3(a1, r), F = dot3(a2, r);
+  double den = A * E - Bq * Bq, s = 0, t;
+  if (den > 1e-30) s = clampd((Bq * F - C * E) / den, -1.0, 1.0);
+  t = (Bq * s + F) / E;
+  if (t < -1.0) { t = -1.0; s = clampd((-Bq - C) / A, -1.0, 1.0); }
+  else if (t > 1.0) { t = 1.0; s = clampd((Bq - C) / A, -1.0, 1.0); }
+  double d[3] = {r[0] + s * a1[0] - t * a2[0], r[1] + s * a1[1] - t * a2[1], r[2] + s * a1[2] - t * a2[2]};
+  return dot3(d, d);
+}
+TSG_FN double ptseg_dist2(const double* c, const double* p, const double* a) {
+  double r[3]; sub3(r, c, p);
+  double t = clampd(dot3(r, a) / dot3(a, a), -1.0, 1.0);
+  addscl3(r, a, -t);
+  return dot3(r, r);
+}
+
+TSG_FN void plane_cylinder_points(const DevModel& m, const double* pos2, const double* axis_in, double radius, double half,
+                                  const double* xaxis, int& cnt, double dist[4], double pts[4][3]) {
+  const double* normal = m.fnormal;
+  double axis[3], vec[3];
+  copy3(axis, axis_in);
+  double prjaxis = dot3(normal, axis);
+  if (prjaxis > 0) { scl3(axis, axis, -1); prjaxis = -prjaxis; }
+  sub3(vec, pos2, m.fpos);
+  double dist0 = dot3(vec, normal);
+  scl3(vec, axis, prjaxis); sub3(vec, vec, normal);
+  double len_sqr = dot3(vec, vec);
+  if (len_sqr >= MINVAL * MINVAL) scl3(vec, vec, radius / sqrt(len_sqr));
+  else scl3(vec, xaxis, radius);
+  double prjvec = dot3(vec, normal);
+  scl3(axis, axis, half); prjaxis *= half;
+  cnt = 0;
+  if (dist0 + prjaxis + prjvec <= 0) {
+    dist[cnt] = dist0 + prjaxis + prjvec;
+    add3(pts[cnt], pos2, vec); add3(pts[cnt], pts[cnt], axis); addscl3(pts[cnt], normal, -dist[cnt] * 0.5);
+    cnt++;
+  } else return;
+  if (dist0 - prjaxis + prjvec <= 0) {
+    dist[cnt] = dist0 - prjaxis + prjvec;
+    add3(pts[cnt], pos2, vec); sub3(pts[cnt], pts[cnt], axis); addscl3(pts[cnt], normal, -dist[cnt] * 0.5);
+    cnt++;
+  }
+  double prjvec1 = -prjvec * 0.5;
+  if (dist0 + prjaxis + prjvec1 <= 0) {
+    double vec1[3];
+    cross3(vec1, vec, axis); normalize3(vec1); scl3(vec1, vec1, radius * sqrt(3.0) * 0.5);
+    for (int s = 0; s < 2; s++) {
+      dist[cnt] = dist0 + prjaxis + prjvec1;
+      add3(pts[cnt], pos2, axis); addscl3(pts[cnt], vec1, s ? -1.0 : 1.0); addscl3(pts[cnt], vec, -0.5);
+      addscl3(pts[cnt], normal, -dist[cnt] * 0.5);
+      cnt++;
+    }
+  }
+}
+
+// floor = plane: analytic plane-sphere / plane-cylinder
+TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
+  LANE_FOR_ALL(g, NGEOM) {
+    int need = 0, cnt = 0;
+    double dist[4], pts[4][3];
+    if (g < NGEOM) {
+      int b = g / 5;
+      const double* c = S.gpos + 3 * g;
+      double tmp[3]; sub3(tmp, c, m.fpos);
+      double cdist = dot3(tmp, m.fnormal);
+      if (m.gtype[g] == GEOM_SPHERE) {
+        double r = m.gsize[g][0];
+        if (cdist <= r) { cnt = 1; dist[0] = cdist - r; copy3(pts[0], c); addscl3(pts[0], m.fnormal, -dist[0] / 2 - r); }
+      } else if (cdist <= sqrt(m.gsize[g][0] * m.gsize[g][0] + m.gsize[g][1] * m.gsize[g][1])) {
+        const double* R = S.xmat + 9 * b;
+        double axis[3] = {R[2], R[5], R[8]}, xaxis[3] = {R[0], R[3], R[6]};
+        plane_cylinder_points(m, c, axis, m.gsize[g][0], m.gsize[g][1], xaxis, cnt, dist, pts);
+      }
+      need = cnt;
+    }
+    int slot = scan_slot(need, nslot, lane);
+    if (need) {
+      int b = g / 5;
+      for (int k = 0; k < cnt; k++) {
+        if (slot + k < MAXC) set_contact(S.con[slot + k], -1, b, dist[k], pts[k], m.fnormal);
+        else S.overflow = 1;
+      }
+    }
+  }
+}
+
+// floor = height field (hfield frame axis-aligned at fpos): geom AABBs -> prism candidates -> MPR
+TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
+  // prism k of row r: vertices n = k, k+1, k+2 of the strip (c = cmin + n/2, i = n%2 -> row r+1 / r)
+  double dx = (2.0 * m.hsize[0]) / (m.ncol - 1), dy = (2.0 * m.hsize[1]) / (m.nrow - 1);
+  for (int j = 0; j < 3; j++) {
+    int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
+    double x = dx * c - m.hsize[0], y = dy * rr - m.hsize[1];
+    double z = (double)m.hdata[rr * m.ncol + c] * m.hsize[2];
+    prism[3 * j] = x; prism[3 * j + 1] = y; prism[3 * j + 2] = -m.hsize[3];
+    prism[9 + 3 * j] = x; prism[10 + 3 * j] = y; prism[11 + 3 * j] = z;
+  }
+}
+TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) {
+  LANE_FOR(g, NGEOM) {
+    int b = g / 5;
+    double pos[3]; sub3(pos, S.gpos + 3 * g, m.fpos);
+    double r = m.gsize[g][0], hl = m.gsize[g][1];
+    double rb = m.gtype[g] == GEOM_SPHERE ? r : sqrt(r * r + hl * hl);
+    bool ok = true;
+    for (int i = 0; i < 2; i++) if (m.hsize[i] < pos[i] - rb || -m.hsize[i] > pos[i] + rb) ok = false;
+    if (m.hsize[2] < pos[2] - rb || -m.hsize[3] > pos[2] + rb) ok = false;
+    double ext[3];
+    if (m.gtype[g] == GEOM_SPHERE) ext[0] = ext[1] = ext[2] = r;
+    else { // AABB half extents of a cylinder = what the +-axis support queries return
+      const double* R = S.xmat + 9 * b;
+      for (int i = 0; i < 3; i++) {
+        double az = R[3 * i + 2];
+        ext[i] = r * sqrt(fmax(0.0, 1.0 - az * az)) + hl * fabs(az);
+      }
+    }
+    double xmin = pos[0] - ext[0], xmax = pos[0] + ext[0], ymin = pos[1] - ext[1], ymax = pos[1] + ext[1];
+    double zmin = pos[2] - ext[2], zmax = pos[2] + ext[2];
+    if (xmin > m.hsize[0] || xmax < -m.hsize[0] || ymin > m.hsize[1] || ymax < -m.hsize[1] || zmin > m.hsize[2] || zmax < -m.hsize[3]) ok = false;
+    int cmin = (int)floor((xmin + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
+    int cmax = (int)ceil((xmax + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
+    int rmin = (int)floor((ymin + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
+    int rmax = (int)ceil((ymax + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
+    if (cmin < 0) cmin = 0;
+    if (cmax > m.ncol - 1) cmax = m.ncol - 1;
+    if (rmin < 0) rmin = 0;
+    if (rmax > m.nrow - 1) rmax = m.nrow - 1;
+    int per_row = 2 * (cmax - cmin + 1) - 2;
+    if (!ok || per_row <= 0 || rmax <= rmin) { per_row = 0; rmax = rmin; }
+    S.hf_cell[g][0] = cmin; S.hf_cell[g][1] = per_row; S.hf_cell[g][2] = rmin; S.hf_cell[g][3] = rmax - rmin;
+    S.hf_zmin[g] = zmin;
+  }
+  WSYNC();
+  // candidates (geom, prism) in MuJoCo's order; chunks of MAXCAND go through MPR in parallel
+  constexpr int PMAX = 24;
+  int ncand = 0;
+  LANE_FOR_ALL(i, NGEOM * PMAX) {
+    int g = i / PMAX, p = i % PMAX, flag = 0;
+    if (g < NGEOM) {
+      int per_row = S.hf_cell[g][1], nrows = S.hf_cell[g][3];
+      if (per_row > 0 && p < per_row * nrows) {
+        int r = S.hf_cell[g][2] + p / per_row, k = p % per_row, cmin = S.hf_cell[g][0];
+        double zmin = S.hf_zmin[g];
+        flag = 0;
+        for (int j = 0; j < 3; j++) {
+          int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
+          if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
+        }
+      } else if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
+    }
+    int slot = scan_slot(flag, ncand, lane);
+    if (flag) { if (slot < MAXCAND) { S.cand[slot] = i; } else S.overflow = 1; }
+  }
+  if (ncand > MAXCAND) ncand = MAXCAND;
+  WSYNC();
+  LANE_FOR_ALL(n, ncand) {
+    bool hit = false;
+    double depth = 0, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
+    int b = 0;
+    if (n < ncand) {
+      int i = S.cand[n], g = i / PMAX, p = i % PMAX;
+      b = g / 5;
+      int per_row = S.hf_cell[g][1];
+      double prism[18];
+      hf_prism(m, S.hf_cell[g][2] + p / per_row, S.hf_cell[g][0], p % per_row, prism);
+      CObj o1, o2;
+      o1.type = 100; o1.prism = prism; o1.mat = nullptr;
+      o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b; o2.prism = nullptr;
+      sub3(o2.pos, S.gpos + 3 * g, m.fpos);
+      o2.size[0] = m.gsize[g][0]; o2.size[1] = m.gsize[g][1];
+      hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, pos);
+      if (hit && ccd_vec_is_origin(dir)) hit = false;
+      if (hit) {
+        add3(pos, pos, m.fpos);
+        if ((m.flags & 4u) && o2.type == GEOM_SPHERE) {
+          double nn[3]; sub3(nn, S.gpos + 3 * g, pos);
+          if (sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(dir, nn); }
+        }
+      }
+    }
+    int slot = scan_slot(hit ? 1 : 0, nslot, lane);
+    if (hit) { if (slot < MAXC) set_contact(S.con[slot], -1, b, -depth, pos, dir); else S.overflow = 1; }
+  }
+  if (lane == 0) S.nmpr_total += ncand;
+  if (nslot > MAXC) nslot = MAXC;
+  WSYNC();
+}
+
+// bar-bar: 75 geom pairs, analytic capsule pre-filter (conservative), then sphere-sphere / MPR
+TSG_FN void collide_bars(Scratch& S, const DevModel& m, int lane, int& nslot) {
+  int ncand = 0;
+  LANE_FOR_ALL(i, 75) {
+    int flag = 0;
+    if (i < 75) {
+      int pr = i / 25, b1 = pr == 2 ? 1 : 0, b2 = pr == 0 ? 1 : 2;
+      int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
+      int t1 = m.gtype[g1], t2 = m.gtype[g2];
+      const double *c1 = S.gpos + 3 * g1, *c2 = S.gpos + 3 * g2;
+      double rs = m.gsize[g1][0] + m.gsize[g2][0] + 1e-6;
+      const double *R1 = S.xmat + 9 * b1, *R2 = S.xmat + 9 * b2;
+      double a1[3] = {R1[2] * m.gsize[g1][1], R1[5] * m.gsize[g1][1], R1[8] * m.gsize[g1][1]};
+      double a2[3] = {R2[2] * m.gsize[g2][1], R2[5] * m.gsize[g2][1], R2[8] * m.gsize[g2][1]};
+      double d2;
+      if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) { double d[3]; sub3(d, c1, c2); d2 = dot3(d, d); }
+      else if (t1 == GEOM_SPHERE) d2 = ptseg_dist2(c1, c2, a2);
+      else if (t2 == GEOM_SPHERE) d2 = ptseg_dist2(c2, c1, a1);
+      else d2 = segseg_dist2(c1, a1, c2, a2);
+      flag = d2 <= rs * rs;
+    }
+    int slot = scan_slot(flag, ncand, lane);
+    if (flag) { if (slot < MAXCAND) S.cand[slot] = i; else S.overflow = 1; }
+  }
+  if (ncand > MAXCAND) ncand = MAXCAND;
+  WSYNC();
+  LANE_FOR_ALL(n, ncand) {
+    bool hit = false;
+    double dist = 1, pos[3] = {0, 0, 0}, nrm[3] = {1, 0, 0};
+    int b1 = 0, b2 = 1;
+    if (n < ncand) {
+      int i = S.cand[n];
+      int pr = i / 25;
+      b1 = pr == 2 ? 1 : 0; b2 = pr == 0 ? 1 : 2;
+      int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
+      if (m.gtype[g1] > m.gtype[g2]) { int t = g1; g1 = g2; g2 = t; t = b1; b1 = b2; b2 = t; }  // lower type first
+      const double *c1 = S.gpos + 3 * g1, *c2 = S.gpos + 3 * g2;
+      if (m.gtype[g2] == GEOM_SPHERE) {
+        sub3(nrm, c2, c1);
+        double len = normalize3(nrm), r1 = m.gsize[g1][0];
+        dist = len - r1 - m.gsize[g2][0];
+        hit = dist <= 0;
+        copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
+      } else {
+        CObj o1, o2;
+        o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; o1.prism = nullptr; copy3(o1.pos, c1);
+        o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
+        o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; o2.prism = nullptr; copy3(o2.pos, c2);
+        o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
+        double depth;
+        hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
+        if (hit && ccd_vec_is_origin(nrm)) hit = false;
+        dist = -depth;
+        if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
+          double nn[3]; sub3(nn, pos, c1);
+          if (sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(nrm, nn); }
+        }
+      }
+    }
+    int slot = scan_slot(hit ? 1 : 0, nslot, lane);
+    if (hit) { if (slot < MAXC) set_contact(S.con[slot], b1, b2, dist, pos, nrm); else S.overflow = 1; }
+  }
+  if (lane == 0) S.nmpr_total += ncand;
+  if (nslot > MAXC) nslot = MAXC;
+  WSYNC();
+}
+
+TSG_FN double impedance(const DevModel& m, double pos) {
+  double d0 = clampd(m.solimp[0], MINIMP, MAXIMP), dw = clampd(m.solimp[1], MINIMP, MAXIMP);
+  double width = fmax(MINVAL, m.solimp[2]), mid = clampd(m.solimp[3], MINIMP, MAXIMP), power = fmax(1.0, m.solimp[4]);
+  if (d0 == dw || width <= MINVAL) return 0.5 * (d0 + dw);
+  double x = fabs(pos) / width, y;
+  if (x >= 1) return dw;
+  if (x == 0) return d0;
+  if (power == 1) y = x;
+  else if (x <= mid) y = (1 / pow(mid, power - 1)) * pow(x, power);
+  else y = 1 - (1 / pow(1 - mid, power - 1)) * pow(1 - x, power);
+  return d0 + y * (dw - d0);
+}
+
+// collision + constraint rows; leaves S.nact active contacts listed in S.order
+TSG_FN void stage_constraint(Scratch& S, const DevModel& m, int lane) {
+  int nslot = 0;
+  if (m.floor_type == 0) { collide_plane(S, m, lane, nslot); if (nslot > MAXC) nslot = MAXC; WSYNC(); }
+  else collide_hfield(S, m, lane, nslot);
+  collide_bars(S, m, lane, nslot);
+  // compact the active slots
+  int nact = 0;
+  LANE_FOR_ALL(s, MAXC) {
+    int flag = (s < nslot) && S.con[s].active;
+    int k = scan_slot(flag, nact, lane);
+    if (flag) S.order[k] = s;
+  }
+  if (lane == 0) { S.nact = nact; S.nslot = nslot; }
+  WSYNC();
+  // Jacobian blocks: item = (contact, side, axis)
+  LANE_FOR(i, nact * 6) {
+    Con& c = S.con[S.order[i / 6]];
+    int side = (i % 6) / 3, ax = i % 3, b = side ? c.b2 : c.b1;
+    double* Jt = c.J[side][ax];
+    double* Jr = c.J[side][3 + ax];
+    if (b < 0) { for (int k = 0; k < 6; k++) { Jt[k] = 0; Jr[k] = 0; } }
+    else {
+      double s = side ? 1.0 : -1.0, rr[3], t[3], w[3];
+      const double* a = c.frame + 3 * ax;
+      sub3(rr, c.pos, S.qpos + 7 * b);
+      cross3(t, rr, a);
+      mulMTV(w, S.xmat + 9 * b, t);
+      Jt[0] = s * a[0]; Jt[1] = s * a[1]; Jt[2] = s * a[2]; Jt[3] = s * w[0]; Jt[4] = s * w[1]; Jt[5] = s * w[2];
+      mulMTV(w, S.xmat + 9 * b, a);
+      Jr[0] = Jr[1] = Jr[2] = 0; Jr[3] = s * w[0]; Jr[4] = s * w[1]; Jr[5] = s * w[2];
+    }
+  }
+  WSYNC();
+  // rows: velocity, impedance, reference acceleration; item = (contact, row)
+  LANE_FOR(i, nact * 6) {
+    Con& c = S.con[S.order[i / 6]];
+    int r = i % 6;
+    double vel = 0;
+    if (c.b1 >= 0) for (int k = 0; k < 6; k++) vel += c.J[0][r][k] * S.qvel[6 * c.b1 + k];
+    for (int k = 0; k < 6; k++) vel += c.J[1][r][k] * S.qvel[6 * c.b2 + k];
+    double imp = impedance(m, c.dist);
+    if (r == 0) {
+      double tran = (c.b1 >= 0 ? m.invw_tran[c.b1] : 0.0) + m.invw_tran[c.b2];
+      c.D0 = 1 / fmax(MINVAL, (1 - imp) / imp * tran);
+    }
+    c.aref[r] = -m.B * vel - (r ? 0.0 : m.K * imp * c.dist);
+  }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------ Newton solver
+TSG_FN void compute_jar(Scratch& S, const double* a, int lane) {
+  LANE_FOR(i, S.nact * 6) {
+    Con& c = S.con[S.order[i / 6]];
+    int r = i % 6;
+    double v = 0;
+    if (c.b1 >= 0) for (int k = 0; k < 6; k++) v += c.J[0][r][k] * a[6 * c.b1 + k];
+    for (int k = 0; k < 6; k++) v += c.J[1][r][k] * a[6 * c.b2 + k];
+    c.jar[r] = v - c.aref[r];
+  }
+  WSYNC();
+}
+// mj_constraintUpdate for one elliptic contact; returns its cost
+TSG_FN double con_update(Con& c, const DevModel& m, bool full) {
+  double U[6], T = 0, mu = m.mu;
+  U[0] = c.jar[0] * mu;
+  for (int j = 1; j < 6; j++) { U[j] = c.jar[j] * m.fr[j - 1]; T += U[j] * U[j]; }
+  double N = U[0];
+  T = sqrt(T);
+  if (N >= mu * T || (T <= 0 && N >= 0)) {
+    if (full) { for (int j = 0; j < 6; j++) { c.force[j] = 0; c.w[j] = 0; } c.zone = ZONE_TOP; c.ca = c.cb = 0; }
+    return 0;
+  }
+  if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+    double s = 0;
+    for (int j = 0; j < 6; j++) {
+      double D = c.D0 * m.dscale[j];
+      s += 0.5 * D * c.jar[j] * c.jar[j];
+      if (full) { c.force[j] = -D * c.jar[j]; c.w[j] = D; }
+    }
+    if (full) { c.zone = ZONE_BOTTOM; c.ca = c.cb = 0; }
+    return s;
+  }
+  double Dm = c.D0 / (mu * mu * (1 + mu * mu)), NT = N - mu * T;
+  if (full) {
+    c.force[0] = -Dm * NT * mu;
+    double kap = mu * mu - mu * N / T;
+    c.w[0] = 0; c.su[0] = 0;
+    for (int j = 1; j < 6; j++) {
+      c.force[j] = -c.force[0] / T * U[j] * m.fr[j - 1];
+      c.w[j] = Dm * kap * m.fr[j - 1] * m.fr[j - 1];
+      c.su[j] = m.fr[j - 1] * U[j] / T;
+    }
+    c.ca = Dm; c.cb = Dm * kap; c.zone = ZONE_MIDDLE;
+  }
+  return 0.5 * Dm * NT * NT;
+}
+// cost of candidate acceleration a: constraint part via S.red, Gauss part added by the caller
+TSG_FN double constraint_cost(Scratch& S, const DevModel& m, int lane, bool full) {
+  LANE_FOR(n, S.nact) S.red[n] = con_update(S.con[S.order[n]], m, full);
+  WSYNC();
+  double s = 0;
+  for (int n = 0; n < S.nact; n++) s += S.red[n];
+  WSYNC();
+  return s;
+}
+TSG_FN double gauss_cost(const Scratch& S, const DevModel& m, const double* a) {
+  double g = 0;
+  for (int k = 0; k < NV; k++) { double d = a[k] - S.asmooth[k]; g += 0.5 * m.M[k] * d * d; }
+  return g;
+}
+// gradient, Hessian, Cholesky, search = -H^-1 grad.  Needs con_update(full) done.
+TSG_FN void newton_direction(Scratch& S, const DevModel& m, int lane) {
+  int nact = S.nact;
+  // cone vectors b = sum_j su_j J_j  (item = contact, side, dof)
+  LANE_FOR(i, nact * 12) {
+    Con& c = S.con[S.order[i / 12]];
+    if (c.zone == ZONE_MIDDLE) {
+      int side = (i % 12) / 6, k = i % 6;
+      double v = 0;
+      for (int j = 1; j < 6; j++) v += c.su[j] * c.J[side][j][k];
+      c.bvec[side][k] = v;
+    }
+  }
+  // gradient + qfrc_constraint (item = dof)
+  LANE_FOR(i, NV) {
+    int b = i / 6, k = i % 6;
+    double f = 0;
+    for (int n = 0; n < nact; n++) {
+      const Con& c = S.con[S.order[n]];
+      int side = c.b2 == b ? 1 : (c.b1 == b ? 0 : -1);
+      if (side < 0) continue;
+      for (int r = 0; r < 6; r++) f += c.J[side][r][k] * c.force[r];
+    }
+    S.fcon[i] = f;
+    S.grad[i] = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
+  }
+  WSYNC();
+  // Hessian lower triangle (item = entry)
+  LANE_FOR(e, NV * (NV + 1) / 2) {
+    int i = 0; while ((i + 1) * (i + 2) / 2 <= e) i++;
+    int j = e - i * (i + 1) / 2;
+    int bi = i / 6, ki = i % 6, bj = j / 6, kj = j % 6;
+    double v = (i == j) ? m.M[i] : 0.0;
+    for (int n = 0; n < nact; n++) {
+      const Con& c = S.con[S.order[n]];
+      if (c.zone == ZONE_TOP) continue;
+      int si = c.b2 == bi ? 1 : (c.b1 == bi ? 0 : -1);
+      int sj = c.b2 == bj ? 1 : (c.b1 == bj ? 0 : -1);
+      if (si < 0 || sj < 0) continue;
+      for (int r = 0; r < 6; r++) v += c.w[r] * c.J[si][r][ki] * c.J[sj][r][kj];
+      if (c.zone == ZONE_MIDDLE) {
+        double bi_ = c.bvec[si][ki], bj_ = c.bvec[sj][kj];
+        double ai = m.mu * (c.J[si][0][ki] - bi_), aj = m.mu * (c.J[sj][0][kj] - bj_);
+        v += c.ca * ai * aj - c.cb * bi_ * bj_;
+      }
+    }
+    S.H[i * HS + j] = v;
+  }
+  LANE_FOR(i, NV) S.rhs[i] = S.grad[i];
+  WSYNC();
+  // Cholesky (row i owned by lane i), then forward / backward substitution
+  for (int k = 0; k < NV; k++) {
+    double piv = sqrt(fmax(S.H[k * HS + k], MINVAL)), inv = 1.0 / piv;
+    LANE_FOR(i, NV) {
+      if (i == k) S.dinv[k] = inv;
+      if (i > k) S.H[i * HS + k] *= inv;
+    }
+    WSYNC();
+    LANE_FOR(i, NV) if (i > k) {
+      double lik = S.H[i * HS + k];
+      for (int j = k + 1; j <= i; j++) S.H[i * HS + j] -= lik * S.H[j * HS + k];
+    }
+    WSYNC();
+  }
+  for (int k = 0; k < NV; k++) {
+    double yk = S.rhs[k] * S.dinv[k];
+    WSYNC();
+    LANE_FOR(i, NV) { if (i == k) S.rhs[k] = yk; else if (i > k) S.rhs[i] -= S.H[i * HS + k] * yk; }
+    WSYNC();
+  }
+  for (int k = NV - 1; k >= 0; k--) {
+    double xk = S.rhs[k] * S.dinv[k];
+    WSYNC();
+    LANE_FOR(i, NV) { if (i == k) S.rhs[k] = xk; else if (i < k) S.rhs[i] -= S.H[k * HS + i] * xk; }
+    WSYNC();
+  }
+  LANE_FOR(i, NV) S.search[i] = -S.rhs[i];
+  WSYNC();
+}
+
+struct LsPnt { double alpha, cost, d0, d1; };
+struct LsCtx { double qG0, qG1, qG2; int parity; int evals; };
+
+TSG_FN void ls_eval(Scratch& S, const DevModel& m, int lane, LsCtx& L, LsPnt& p) {
+  double a = p.alpha, mu = m.mu;
+  int par = L.parity; L.parity ^= 1;
+  LANE_FOR(n, S.nact) {
+    const Con& c = S.con[S.order[n]];
+    double cost = 0, d0 = 0, d1 = 0;
+    double N = c.U0 + a * c.V0, Tsqr = c.UU + a * (2 * c.UV + a * c.VV);
+    bool bottom = false;
+    if (Tsqr <= 0) { if (N < 0) bottom = true; }
+    else {
+      double T = sqrt(Tsqr);
+      if (N >= mu * T) {}
+      else if (mu * N + T <= 0) bottom = true;
+      else {
+        double N1 = c.V0, T1 = (c.UV + a * c.VV) / T;
+        double T2 = c.VV / T - (c.UV + a * c.VV) * T1 / (T * T);
+        double NT = N - mu * T, Dm = c.D0 / (mu * mu * (1 + mu * mu));
+        cost = 0.5 * Dm * NT * NT;
+        d0 = Dm * NT * (N1 - mu * T1);
+        d1 = Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NT * (-mu * T2));
+      }
+    }
+    if (bottom) { cost = a * a * c.q2 + a * c.q1 + c.q0; d0 = 2 * a * c.q2 + c.q1; d1 = 2 * c.q2; }
+    S.lsacc[par][n][0] = cost; S.lsacc[par][n][1] = d0; S.lsacc[par][n][2] = d1;
+  }
+  WSYNC();
+  double cost = a * a * L.qG2 + a * L.qG1 + L.qG0, d0 = 2 * a * L.qG2 + L.qG1, d1 = 2 * L.qG2;
+  for (int n = 0; n < S.nact; n++) { cost += S.lsacc[par][n][0]; d0 += S.lsacc[par][n][1]; d1 += S.lsacc[par][n][2]; }
+  if (d1 <= 0) d1 = MINVAL;
+  p.cost = cost; p.d0 = d0; p.d1 = d1;
+  L.evals++;
+}
+TSG_FN int ls_update_bracket(Scratch& S, const DevModel& m, int lane, LsCtx& L, LsPnt& p, const LsPnt* cand, LsPnt& pnext) {
+  int flag = 0;
+  for (int i = 0; i < 3; i++) {
+    if (p.d0 < 0 && cand[i].d0 < 0 && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
+    else if (p.d0 > 0 && cand[i].d0 > 0 && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
+  }
+  if (flag) { pnext.alpha = p.alpha - p.d0 / p.d1; ls_eval(S, m, lane, L, pnext); }
+  return flag;
+}
+// exact line search along S.search from S.qacc (jar current); returns alpha. gauss = current Gauss cost
+TSG_FN double line_search(Scratch& S, const DevModel& m, int lane, double gauss, int& evals_out) {
+  double snorm = 0;
+  for (int k = 0; k < NV; k++) snorm += S.search[k] * S.search[k];
+  snorm = sqrt(snorm);
+  evals_out = 0;
+  if (snorm < MINVAL) return 0;
+  double scale = 1 / (m.meaninertia * NV);
+  double gtol = m.tol * m.ls_tol * snorm / scale;
+  LsCtx L; L.parity = 0; L.evals = 0;
+  L.qG0 = gauss; L.qG1 = 0; L.qG2 = 0;
+  for (int k = 0; k < NV; k++) {
+    L.qG1 += S.search[k] * (m.M[k] * S.qacc[k]) - S.fsm[k] * S.search[k];
+    L.qG2 += 0.5 * S.search[k] * (m.M[k] * S.search[k]);
+  }
+  // jv = J search ; per-contact quadratic / cone coefficients
+  LANE_FOR(i, S.nact * 6) {
+    Con& c = S.con[S.order[i / 6]];
+    int r = i % 6;
+    double v = 0;
+    if (c.b1 >= 0) for (int k = 0; k < 6; k++) v += c.J[0][r][k] * S.search[6 * c.b1 + k];
+    for (int k = 0; k < 6; k++) v += c.J[1][r][k] * S.search[6 * c.b2 + k];
+    c.jv[r] = v;
+  }
+  WSYNC();
+  LANE_FOR(n, S.nact) {
+    Con& c = S.con[S.order[n]];
+    double q0 = 0, q1 = 0, q2 = 0, UU = 0, UV = 0, VV = 0;
+    for (int j = 0; j < 6; j++) {
+      double D = c.D0 * m.dscale[j], ja = c.jar[j], jv = c.jv[j];
+      q0 += 0.5 * D * ja * ja; q1 += D * ja * jv; q2 += 0.5 * D * jv * jv;
+      if (j > 0) { double U = ja * m.fr[j - 1], V = jv * m.fr[j - 1]; UU += U * U; UV += U * V; VV += V * V; }
+    }
+    c.q0 = q0; c.q1 = q1; c.q2 = q2;
+    c.U0 = c.jar[0] * m.mu; c.V0 = c.jv[0] * m.mu; c.UU = UU; c.UV = UV; c.VV = VV;
+  }
+  WSYNC();
+  LsPnt p0, p1, p2, pmid, p1next, p2next;
+  double result;
+  p0.alpha = 0; ls_eval(S, m, lane, L, p0);
+  p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(S, m, lane, L, p1);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabs(p1.d0) < gtol) { evals_out = L.evals; return p1.alpha; }
+  int dir = p1.d0 < 0 ? 1 : -1, p2update = 0;
+  p2 = p1;
+  while (p1.d0 * dir <= -gtol && L.evals < m.ls_iterations) {
+    p2 = p1; p2update = 1;
+    p1.alpha -= p1.d0 / p1.d1; ls_eval(S, m, lane, L, p1);
+    if (fabs(p1.d0) < gtol) { evals_out = L.evals; return p1.alpha; }
+  }
+  if (L.evals >= m.ls_iterations || !p2update) { evals_out = L.evals; return p1.alpha; }
+  p2next = p1;
+  p1next.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(S, m, lane, L, p1next);
+  bool done = false;
+  result = 0;
+  while (L.evals < m.ls_iterations) {
+    pmid.alpha = 0.5 * (p1.alpha + p2.alpha); ls_eval(S, m, lane, L, pmid);
+    LsPnt cand[3] = {p1next, p2next, pmid};
+    int best = -1; double bestcost = 0;
+    for (int i = 0; i < 3; i++)
+      if (fabs(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
+    if (best >= 0) { result = cand[best].alpha; done = true; break; }
+    int b1 = ls_update_bracket(S, m, lane, L, p1, cand, p1next);
+    int b2 = ls_update_bracket(S, m, lane, L, p2, cand, p2next);
+    if (!b1 && !b2) { result = pmid.alpha; done = true; break; }
+  }
+  if (!done) {
+    if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
+    else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
+    else result = 0;
+  }
+  evals_out = L.evals;
+  return result;
+}
+
+// mj_fwdConstraint: warm-start choice + Newton iterations.  Leaves S.qacc, S.fcon, S.warm.
+TSG_FN void stage_solve(Scratch& S, const DevModel& m, int lane) {
+  if (S.nact == 0) {
+    LANE_FOR(i, NV) { S.qacc[i] = S.asmooth[i]; S.warm[i] = S.asmooth[i]; S.fcon[i] = 0; }
+    WSYNC();
+    return;
+  }
+  // cost at qacc_smooth (Gauss term 0), then at the warm start
+  compute_jar(S, S.asmooth, lane);
+  double cost_sm = constraint_cost(S, m, lane, false);
+  compute_jar(S, S.warm, lane);
+  double cost_ws = constraint_cost(S, m, lane, false) + gauss_cost(S, m, S.warm);
+  bool use_smooth = cost_ws > cost_sm;
+  LANE_FOR(i, NV) S.qacc[i] = use_smooth ? S.asmooth[i] : S.warm[i];
+  WSYNC();
+  if (use_smooth) compute_jar(S, S.qacc, lane);
+  double gauss = gauss_cost(S, m, S.qacc);
+  double cost = constraint_cost(S, m, lane, true) + gauss;
+  newton_direction(S, m, lane);
+  double scale = 1 / (m.meaninertia * NV);
+  int iter = 0, nls = 0;
+  while (iter < m.iterations) {
+    int ev;
+    double alpha = line_search(S, m, lane, gauss, ev);
+    nls += ev;
+    if (alpha == 0) break;
+    WSYNC();
+    LANE_FOR(i, NV + S.nact * 6) {
+      if (i < NV) S.qacc[i] += alpha * S.search[i];
+      else { int n = (i - NV) / 6, r = (i - NV) % 6; Con& c = S.con[S.order[n]]; c.jar[r] += alpha * c.jv[r]; }
+    }
+    WSYNC();
+    double oldcost = cost;
+    gauss = gauss_cost(S, m, S.qacc);
+    cost = constraint_cost(S, m, lane, true) + gauss;
+    newton_direction(S, m, lane);
+    double gn = 0;
+    for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
+    double improvement = scale * (oldcost - cost), gradient = scale * sqrt(gn);
+    iter++;
+    if (improvement < m.tol || gradient < m.tol) break;
+  }
+  WSYNC();
+  LANE_FOR(i, NV) S.warm[i] = S.qacc[i];
+  if (lane == 0) { S.niter_total += iter; S.nls_total += nls; }
+  WSYNC();
+}
+
+// ------------------------------------------------------------------ implicitfast + advance
+TSG_FN void stage_integrate(Scratch& S, const DevModel& m, int lane) {
+  double h = m.h;
+  LANE_FOR(b, NBAR) {
+    double A[21], x[6];
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c <= r; c++) {
+        int t = r * (r + 1) / 2 + c;
+        A[t] = -h * S.Dblk[b][t] + (r == c ? m.M[6 * b + r] : 0.0);
+      }
+    for (int k = 0; k < 6; k++) x[k] = S.fsm[6 * b + k] + S.fcon[6 * b + k];
+    for (int j = 0; j < 6; j++) {
+      double s = A[j * (j + 1) / 2 + j];
+      for (int k = 0; k < j; k++) s -= A[j * (j + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
+      double piv = sqrt(s);
+      A[j * (j + 1) / 2 + j] = piv;
+      for (int i = j + 1; i < 6; i++) {
+        double t = A[i * (i + 1) / 2 + j];
+        for (int k = 0; k < j; k++) t -= A[i * (i + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
+        A[i * (i + 1) / 2 + j] = t / piv;
+      }
+    }
+    for (int i = 0; i < 6; i++) { double t = x[i]; for (int k = 0; k < i; k++) t -= A[i * (i + 1) / 2 + k] * x[k]; x[i] = t / A[i * (i + 1) / 2 + i]; }
+    for (int i = 5; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 6; k++) t -= A[k * (k + 1) / 2 + i] * x[k]; x[i] = t / A[i * (i + 1) / 2 + i]; }
+    double* v = S.qvel + 6 * b; double* q = S.qpos + 7 * b;
+    for (int k = 0; k < 6; k++) v[k] += h * x[k];
+    for (int k = 0; k < 3; k++) q[k] += h * v[k];
+    double ax[3] = {v[3], v[4], v[5]}, qr[4], qn[4];
+    double ang = h * normalize3(ax);
+    if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
+    else { double s = sin(ang * 0.5); qr[0] = cos(ang * 0.5); qr[1] = ax[0] * s; qr[2] = ax[1] * s; qr[3] = ax[2] * s; }
+    normalize4(q + 3);
+    const double* a = q + 3;
+    qn[0] = a[0] * qr[0] - a[1] * qr[1] - a[2] * qr[2] - a[3] * qr[3];
+    qn[1] = a[0] * qr[1] + a[1] * qr[0] + a[2] * qr[3] - a[3] * qr[2];
+    qn[2] = a[0] * qr[2] - a[1] * qr[3] + a[2] * qr[0] + a[3] * qr[1];
+    qn[3] = a[0] * qr[3] + a[1] * qr[2] - a[2] * qr[1] + a[3] * qr[0];
+    q[3] = qn[0]; q[4] = qn[1]; q[5] = qn[2]; q[6] = qn[3];
+  }
+  if (m.dyntype) { LANE_FOR(i, NACT) S.act[i] += h * S.actdot[i]; }
+  WSYNC();
+}
+
+TSG_FN void reset_data(Scratch& S, const DevModel& m, int lane) {  // mj_resetData
+  LANE_FOR(i, NQ) S.qpos[i] = m.qpos0[i];
+  LANE_FOR(i, NV) { S.qvel[i] = 0; S.warm[i] = 0; }
+  LANE_FOR(i, NACT) { S.ctrl[i] = 0; S.act[i] = 0; }
+  WSYNC();
+}
+// mj_forward
+TSG_FN_NOINLINE void forward(CTX_PARAMS) {
+  CTX_BIND
+  stage_position(S, m, lane);
+  stage_tendon(S, m, lane);
+  stage_smooth(S, m, lane);
+  stage_constraint(S, m, lane);
+  stage_solve(S, m, lane);
+}
+// one mj_step
+TSG_FN_NOINLINE void substep(CTX_PARAMS) {
+  CTX_BIND
+  // mj_checkPos / mj_checkVel
+  bool bad = false;
+  for (int i = 0; i < NQ; i++) bad |= is_bad(S.qpos[i]);
+  for (int i = 0; i < NV; i++) bad |= is_bad(S.qvel[i]);
+  WSYNC();
+  if (bad) { if (lane == 0) S.bad |= 1; reset_data(S, m, lane); }
+  forward(CTX_ARGS);
+  bad = false;
+  for (int i = 0; i < NV; i++) bad |= is_bad(S.qacc[i]);  // mj_checkAcc
+  WSYNC();
+  if (bad) { if (lane == 0) S.bad |= 4; reset_data(S, m, lane); forward(CTX_ARGS); }
+  stage_integrate(S, m, lane);
+}
+
+// mj_rnePostConstraint: cfrc_ext rows [torque; force] for world + 3 bars, from the last forward pass
+TSG_FN void stage_cfrc(Scratch& S, const DevModel& m, int lane) {
+  LANE_FOR(i, 24) {
+    int body = i / 6, comp = i % 6;  // body 0 = world
+    double com[3];
+    if (body == 0) {
+      double mt = 0; com[0] = com[1] = com[2] = 0;
+      for (int b = 0; b < NBAR; b++) { addscl3(com, S.xstale + 3 * b, m.M[6 * b]); mt += m.M[6 * b]; }
+      scl3(com, com, 1 / mt);
+    } else copy3(com, S.xstale + 3 * (body - 1));
+    double acc = 0;
+    for (int n = 0; n < S.nact; n++) {
+      const Con& c = S.con[S.order[n]];
+      double s;
+      if (c.b2 == body - 1) s = 1; else if (c.b1 == body - 1) s = -1; else continue;
+      double F[3], T[3];
+      mulMTV(F, c.frame, c.force); mulMTV(T, c.frame, c.force + 3);
+      if (comp >= 3) acc += s * F[comp - 3];
+      else { double r[3], tq[3]; sub3(r, c.pos, com); cross3(tq, r, F); acc += s * (tq[comp] + T[comp]); }
+    }
+    S.cfrc[body][comp] = acc;
+  }
+  WSYNC();
+}
+
+}  // namespace tsg

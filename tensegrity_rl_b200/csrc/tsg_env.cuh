@@ -1,0 +1,502 @@
+// tsg_env.cuh -- tr_env / tensegrity_env semantics around the physics core, per warp.
+//   step    : tr_env.py:327-527 ; tensegrity_env.py:291-410
+//   obs     : tr_env.py:529-646 ; tensegrity_env.py:412-430
+//   reset   : tr_env.py:709-872 ; tensegrity_env.py:433-512  (+ gym MujocoEnv.reset / set_state)
+#pragma once
+#include "tsg_core.cuh"
+
+namespace tsg {
+
+constexpr double PI = 3.14159265358979323846;
+enum { ENV_TR = 0, ENV_LEGACY = 1 };
+enum { TASK_STRAIGHT = 0, TASK_TURN = 1, TASK_AIMING = 2, TASK_TRACKING = 3, TASK_VEL_TRACK = 4 };
+
+struct Aux {  // warp-uniform env bookkeeping kept in registers
+  double xy_prev[2], psi_prev, reset_psi, waypt[2], ori[2];
+  double step_num, ep_ret, ep_len, xvel, yvel;
+  int head_n, head_pos;
+};
+struct StepOut {  // warp-uniform results of one env step
+  double reward, fwd, ctrl_cost, healthy, psi, xy[2];
+  int terminated;
+  double maxcfrc, barforce;
+};
+
+TSG_FN double angle_normalize(double t) {  // tr_env.py:648-654
+  while (t > PI) t -= 2 * PI;
+  while (t <= -PI) t += 2 * PI;
+  return t;
+}
+
+struct Pose { double xy[2], left[3], right[3], psi; };
+// COM / left-right end-cap centroids from the (stale) kinematics of the last forward pass
+TSG_FN void read_pose(const Scratch& S, Pose& P) {
+  P.xy[0] = (S.xstale[0] + S.xstale[3] + S.xstale[6]) / 3;
+  P.xy[1] = (S.xstale[1] + S.xstale[4] + S.xstale[7]) / 3;
+  for (int k = 0; k < 3; k++) {
+    P.left[k] = (S.gpos[3 * 1 + k] + S.gpos[3 * 6 + k] + S.gpos[3 * 11 + k]) / 3;   // s0, s2, s4
+    P.right[k] = (S.gpos[3 * 2 + k] + S.gpos[3 * 7 + k] + S.gpos[3 * 12 + k]) / 3;  // s1, s3, s5
+  }
+  P.psi = atan2(-(P.left[0] - P.right[0]), P.left[1] - P.right[1]);
+}
+
+TSG_FN double ditch_reward(const EnvCfg& c, const Aux& A, const double* xy) {  // tr_env.py:656-667
+  double pv[2] = {A.waypt[0] - A.ori[0], A.waypt[1] - A.ori[1]};
+  double dp = sqrt(pv[0] * pv[0] + pv[1] * pv[1]);
+  double pn[2] = {pv[0] / dp, pv[1] / dp};
+  double tv[2] = {A.waypt[0] - xy[0], A.waypt[1] - xy[1]};
+  double along = tv[0] * pn[0] + tv[1] * pn[1];
+  double bx = tv[0] - along * pn[0], by = tv[1] - along * pn[1];
+  double bias = sqrt(bx * bx + by * by);
+  double ditch = c.ditch_reward_max * (1.0 - fabs(along) / dp) * exp(-(bias * bias) / (2 * c.ditch_reward_stdev * c.ditch_reward_stdev));
+  double dx = xy[0] - A.waypt[0], dy = xy[1] - A.waypt[1];
+  double dn = sqrt(dx * dx + dy * dy);
+  double wp = c.waypt_reward_amplitude * exp(-(dn * dn) / (2 * c.waypt_reward_stdev * c.waypt_reward_stdev));
+  return ditch + wp;
+}
+
+// scipy Rotation.from_matrix(M).as_quat() -> (x, y, z, w)
+TSG_FN void mat2quat_scipy(const double* M, double* q) {
+  double tr = M[0] + M[4] + M[8];
+  double dec[4] = {M[0], M[4], M[8], tr};
+  int ch = 0;
+  for (int i = 1; i < 4; i++) if (dec[i] > dec[ch]) ch = i;
+  if (ch != 3) {
+    int i = ch, j = (i + 1) % 3, k = (j + 1) % 3;
+    q[i] = 1 - tr + 2 * M[4 * i];
+    q[j] = M[3 * j + i] + M[3 * i + j];
+    q[k] = M[3 * k + i] + M[3 * i + k];
+    q[3] = M[3 * k + j] - M[3 * j + k];
+  } else {
+    q[0] = M[7] - M[5]; q[1] = M[2] - M[6]; q[2] = M[3] - M[1]; q[3] = 1 + tr;
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) q[i] /= n;
+}
+
+// observation into S.obs (stale positions / tendon lengths, fresh qvel)
+TSG_FN void compute_obs(EnvScratch& S, const DevModel& m, const EnvCfg& c, const Aux& A, int lane) {
+  if (c.env_kind == ENV_LEGACY) {
+    LANE_FOR(i, 39) {
+      if (i < 12) {
+        if (i % 4 == 0) {  // geom rXY: body frame with x, y columns negated (geom quat 0 0 0 1)
+          int b = i / 4; const double* R = S.xmat + 9 * b;
+          double G[9] = {-R[0], -R[1], R[2], -R[3], -R[4], R[5], -R[6], -R[7], R[8]}, q[4];
+          mat2quat_scipy(G, q);
+          for (int k = 0; k < 4; k++) S.obs[i + k] = q[k];
+        }
+      } else if (i < 30) S.obs[i] = S.qvel[i - 12];
+      else S.obs[i] = S.tlen[i - 30];
+    }
+    WSYNC();
+    return;
+  }
+  double cen[3] = {0, 0, 0};
+  for (int b = 0; b < NBAR; b++)
+    for (int k = 0; k < 3; k++) cen[k] += S.gpos[3 * (5 * b + 1) + k] + S.gpos[3 * (5 * b + 2) + k];
+  for (int k = 0; k < 3; k++) cen[k] /= 6;
+  int nvel = c.use_cap_velocity ? 18 : 0;
+  LANE_FOR(i, 18 + nvel + 9) {
+    if (i < 18) { int cap = i / 3, k = i % 3, g = 5 * (cap / 2) + 1 + (cap % 2); S.obs[i] = S.gpos[3 * g + k] - cen[k]; }
+    else if (i < 18 + nvel) {
+      int j = i - 18, cap = j / 3, k = j % 3, b = cap / 2, g = 5 * b + 1 + (cap % 2);
+      double r[3], w[3] = {S.qvel[6 * b + 3], S.qvel[6 * b + 4], S.qvel[6 * b + 5]}, cr[3];
+      sub3(r, S.gpos + 3 * g, S.xstale + 3 * b);
+      cross3(cr, w, r);  // local-frame angular velocity used as if world-frame (tr_env.py:599-604)
+      S.obs[i] = S.qvel[6 * b + k] + cr[k];
+    } else S.obs[i] = S.tlen[i - 18 - nvel];
+  }
+  int base = 27 + nvel;
+  if (c.task == TASK_TRACKING || c.task == TASK_AIMING) {
+    double tx = A.waypt[0] - cen[0], ty = A.waypt[1] - cen[1], n = sqrt(tx * tx + ty * ty);
+    if (lane == 0) { S.obs[base] = tx; S.obs[base + 1] = ty; S.obs[base + 2] = atan2(ty / n, tx / n); }
+  } else if (c.task == TASK_VEL_TRACK) {
+    if (lane == 0) { S.obs[base] = 0.5 * cos(A.reset_psi); S.obs[base + 1] = 0.5 * sin(A.reset_psi); S.obs[base + 2] = 0.0; }
+  }
+  WSYNC();
+}
+
+// do_simulation(ctrl, frame_skip): ctrl already in S.ctrl
+TSG_FN_NOINLINE void simulate(CTX_PARAMS) {
+  CTX_BIND
+  for (int s = 0; s < c.frame_skip; s++) substep(CTX_ARGS);
+  stage_cfrc(S, m, lane);
+}
+
+TSG_FN void heading_push(EnvScratch& S, Aux& A, double v, int lane) {
+  if (lane == 0) S.heading[(A.head_pos + A.head_n) % HEADING_SLOTS] = v;
+  A.head_n++;
+  WSYNC();
+}
+TSG_FN double heading_pop(EnvScratch& S, Aux& A) {
+  double v = S.heading[A.head_pos];
+  A.head_pos = (A.head_pos + 1) % HEADING_SLOTS;
+  A.head_n--;
+  return v;
+}
+
+// one env.step(action) with action in S.action; updates S, A; obs NOT computed here
+TSG_FN_NOINLINE void env_step(Aux& A, StepOut& O, CTX_PARAMS) {
+  CTX_BIND
+  double dt = c.dt;
+  double xy_before[2] = {A.xy_prev[0], A.xy_prev[1]}, psi_before = A.psi_prev;
+  if (c.env_kind == ENV_TR) {  // _action_filter, k_FILTER = 1 (tr_env.py:680-683)
+    LANE_FOR(i, NACT) S.ctrl[i] = S.ctrl[i] + 1.0 * (S.action[i] - S.ctrl[i]) * dt;
+  } else {
+    LANE_FOR(i, NACT) S.ctrl[i] = S.action[i];
+  }
+  WSYNC();
+  simulate(CTX_ARGS);
+  Pose P; read_pose(S, P);
+  double xvel = (P.xy[0] - xy_before[0]) / dt, yvel = (P.xy[1] - xy_before[1]) / dt;
+  A.xvel = xvel; A.yvel = yvel;
+  double psi_after = P.psi;
+  if (c.env_kind == ENV_LEGACY && c.task == TASK_TURN)  // tensegrity_env.py:320-322
+    psi_after = atan2(P.right[1] - P.left[1], P.right[0] - P.left[0]);
+  double psi_info = psi_after;
+  // control cost
+  double cc = 0;
+  for (int i = 0; i < NACT; i++) {
+    double a = S.action[i];
+    double v = (c.env_kind == ENV_TR) ? (a + 0.5 - S.tlen[i]) : a;
+    cc += v * v;
+  }
+  cc *= c.ctrl_cost_weight;
+  double fwd = 0, ctrl_cost = cc;
+  double healthy = c.terminate_when_unhealthy ? c.healthy_reward : 0.0;
+  int delay = c.reward_delay_steps;
+  bool finite = true;
+  for (int i = 0; i < NQ; i++) finite &= isfinite(S.qpos[i]);
+  for (int i = 0; i < NV; i++) finite &= isfinite(S.qvel[i]);
+  bool moving_any = false;
+  for (int i = 0; i < NV; i++) moving_any |= fabs(S.qvel[i]) > 0.1;
+  bool healthy_turn = finite && moving_any;
+  bool healthy_lin = finite && ((xvel > 1e-4 || xvel < -1e-4) || (yvel > 1e-4 || yvel < -1e-4));
+  bool is_healthy = healthy_lin;
+  bool extra_term = false;
+  if (c.task == TASK_TURN) {
+    is_healthy = healthy_turn;
+    heading_push(S, A, psi_after, lane);
+    if (A.head_n > delay) {
+      double old_psi = heading_pop(S, A), pa = psi_after;
+      if (pa < -PI / 2 && old_psi > PI / 2) pa = 2 * PI + pa;
+      else if (pa > PI / 2 && old_psi < -PI / 2) pa = -2 * PI + pa;
+      if (c.env_kind == ENV_TR) psi_info = pa;  // tr_env rebinds psi_after, legacy too
+      else psi_info = pa;
+      fwd = (pa - old_psi) / (dt * delay) * c.desired_direction;
+    } else { fwd = 0; ctrl_cost = 0; }
+  } else if (c.task == TASK_STRAIGHT) {
+    double dx = P.xy[0] - xy_before[0], dy = P.xy[1] - xy_before[1];
+    double psi_diff = fabs(atan2(dy, dx) - A.reset_psi);
+    fwd = c.desired_direction * (sqrt(dx * dx + dy * dy) * cos(psi_diff) / dt);
+  } else if (c.task == TASK_AIMING) {
+    is_healthy = healthy_turn;
+    double tx = A.waypt[0] - xy_before[0], ty = A.waypt[1] - xy_before[1], n = sqrt(tx * tx + ty * ty);
+    double target_psi = atan2(ty / n, tx / n);
+    double newp = angle_normalize(target_psi - psi_after);
+    heading_push(S, A, newp, lane);
+    if (A.head_n > delay) {
+      double oldp = heading_pop(S, A);
+      fwd = -(fabs(newp) - fabs(oldp)) / (dt * delay) * c.yaw_reward_weight;
+    }
+    healthy = 0;
+    extra_term = A.step_num > 1000;
+  } else if (c.task == TASK_TRACKING) {
+    fwd = ditch_reward(c, A, P.xy) - ditch_reward(c, A, xy_before);
+    healthy = 0;
+    extra_term = A.step_num > 1000;
+  } else {  // vel_track, tr_env.py:461-474, 669-678
+    double ang = angle_normalize(psi_after - psi_before) / dt;
+    double cx = 0.5 * cos(A.reset_psi), cy = 0.5 * sin(A.reset_psi);
+    double le = sqrt((xvel - cx) * (xvel - cx) + (yvel - cy) * (yvel - cy)), ae = ang - 0.0;
+    fwd = 1.0 * exp(-5.0 * le * le) + 0.5 * exp(-7.0 * ae * ae);
+  }
+  bool terminated = c.terminate_when_unhealthy ? !is_healthy : false;
+  if (extra_term) terminated = true;
+  double maxc = 0;
+  for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs(S.cfrc[i / 6][i % 6]));
+  if (maxc > c.kill_force) terminated = true;  // tr_env.py:480-481
+  double barf = 0;  // run.py:155-161 total bar-bar contact force magnitude
+  for (int n = 0; n < S.nact; n++) {
+    const Con& k = S.con[S.order[n]];
+    if (k.b1 >= 0) barf += sqrt(k.force[0] * k.force[0] + k.force[1] * k.force[1] + k.force[2] * k.force[2]);
+  }
+  O.reward = fwd + healthy - ctrl_cost;
+  O.fwd = fwd; O.ctrl_cost = ctrl_cost; O.healthy = healthy; O.psi = psi_info;
+  O.xy[0] = P.xy[0]; O.xy[1] = P.xy[1];
+  O.terminated = terminated ? 1 : 0; O.maxcfrc = maxc; O.barforce = barf;
+  A.step_num += 1;
+  A.xy_prev[0] = P.xy[0]; A.xy_prev[1] = P.xy[1]; A.psi_prev = P.psi;
+}
+
+// refresh the "stale" pose bookkeeping after a forward pass (set_state)
+TSG_FN void aux_from_forward(const Scratch& S, Aux& A) {
+  Pose P; read_pose(S, P);
+  A.xy_prev[0] = P.xy[0]; A.xy_prev[1] = P.xy[1]; A.psi_prev = P.psi;
+}
+
+// env.reset(): MujocoEnv.reset (mj_resetData) + reset_model.  Random draws in S.draws.
+TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
+  const double* u = S.draws;
+  reset_data(S, m, lane);
+  int idx = (int)floor(u[0] * c.npose);
+  if (idx > c.npose - 1) idx = c.npose - 1;
+  if (idx < 0) idx = 0;
+  bool extra_set_state = (c.env_kind == ENV_TR) ? (c.task == TASK_TURN || c.task == TASK_TRACKING || c.task == TASK_AIMING)
+                                                 : (c.task == TASK_TURN);
+  int nfwd = (c.env_kind == ENV_TR ? 1 : 0) + (extra_set_state ? 1 : 0);
+  LANE_FOR(i, NQ) S.qpos[i] = c.reset_pose[idx][i];
+  WSYNC();
+  for (int k = 0; k < nfwd; k++) forward(CTX_ARGS);  // set_state -> mj_forward
+  // rotate the whole robot about world z by theta (positions and orientations)
+  double theta = c.min_reset_heading + u[1] * (c.max_reset_heading - c.min_reset_heading);
+  double ct = cos(theta), st = sin(theta), ch = cos(0.5 * theta), sh = sin(0.5 * theta);
+  LANE_FOR(b, NBAR) {
+    // start again from the table pose: mj_kinematics normalised qpos in place, the reference re-uses its own copy
+    double p[7];
+    for (int k = 0; k < 7; k++) p[k] = c.reset_pose[idx][7 * b + k];
+    double* q = S.qpos + 7 * b;
+    q[0] = ct * p[0] - st * p[1]; q[1] = st * p[0] + ct * p[1]; q[2] = p[2];
+    double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
+    double w = p[3] / n, x = p[4] / n, y = p[5] / n, z = p[6] / n;
+    q[3] = ch * w - sh * z; q[4] = ch * x - sh * y; q[5] = ch * y + sh * x; q[6] = ch * z + sh * w;  // q_z(theta) * q
+  }
+  WSYNC();
+  forward(CTX_ARGS);
+  aux_from_forward(S, A);
+  // tendon set-points
+  LANE_FOR(i, NACT) {
+    double t = u[2 + i] * c.tendon_reset_stdev + c.tendon_reset_mean;
+    if (t > c.tendon_max_length) t = c.tendon_max_length; else if (t < c.tendon_min_length) t = c.tendon_min_length;
+    S.action[i] = t;
+  }
+  WSYNC();
+  StepOut O;
+  if (c.env_kind == ENV_TR) {
+    LANE_FOR(i, NACT) S.ctrl[i] = S.action[i];
+    WSYNC();
+    for (int k = 0; k < c.warmup_steps; k++) simulate(CTX_ARGS);  // do_simulation, no filter
+    aux_from_forward(S, A);
+  } else {
+    for (int k = 0; k < c.warmup_steps; k++) env_step(A, O, CTX_ARGS);  // full self.step
+  }
+  Pose P; read_pose(S, P);
+  A.reset_psi = P.psi;
+  double lo = c.waypt_range[0], hi = c.waypt_range[1];
+  if (c.env_kind == ENV_TR && c.task == TASK_TRACKING) {
+    A.ori[0] = (P.left[0] + P.right[0]) / 2; A.ori[1] = (P.left[1] + P.right[1]) / 2;
+    double len = lo + u[8] * (hi - lo);
+    double yaw = c.waypt_angle_range[0] + u[9] * (c.waypt_angle_range[1] - c.waypt_angle_range[0]) + A.reset_psi;
+    if (c.is_test) { len = 0.5 * hi + 0.5 * lo; yaw = (0.5 * c.waypt_angle_range[1] + 0.5 * c.waypt_angle_range[0]) + A.reset_psi; }
+    A.waypt[0] = A.ori[0] + len * cos(yaw); A.waypt[1] = A.ori[1] + len * sin(yaw);
+  } else if (c.env_kind == ENV_TR && c.task == TASK_AIMING) {
+    A.ori[0] = P.left[0] + P.right[0] / 2;  // operator-precedence quirk kept (tr_env.py:843)
+    A.ori[1] = (P.left[1] + P.right[1]) / 2;
+    double len = lo + u[8] * (hi - lo);
+    double yaw = -PI + u[9] * (2 * PI) + A.reset_psi;
+    if (c.is_test) { len = 0.5 * hi + 0.5 * lo; yaw = (0.75 * PI + 0.25 * (-PI)) + A.reset_psi; }
+    A.waypt[0] = A.ori[0] + len * cos(yaw); A.waypt[1] = A.ori[1] + len * sin(yaw);
+    if (c.is_test) { A.waypt[0] = 0; A.waypt[1] = 0; }
+  }
+  A.step_num = 0;
+  if (c.env_kind == ENV_TR && (c.task == TASK_TURN || c.task == TASK_AIMING))
+    for (int k = 0; k < c.reward_delay_steps; k++) env_step(A, O, CTX_ARGS);
+  A.ep_ret = 0; A.ep_len = 0;
+}
+
+// ---- state record <-> scratch
+TSG_FN void load_env(EnvScratch& S, Aux& A, const double* rec, const double* head, bool need_head, int lane) {
+  LANE_FOR(i, SO_XY_PREV) {
+    double v = rec[i];
+    if (i < SO_QVEL) S.qpos[i] = v;
+    else if (i < SO_WARM) S.qvel[i - SO_QVEL] = v;
+    else if (i < SO_CTRL) S.warm[i - SO_WARM] = v;
+    else if (i < SO_ACT) S.ctrl[i - SO_CTRL] = v;
+    else S.act[i - SO_ACT] = v;
+  }
+  if (need_head) { LANE_FOR(i, HEADING_SLOTS) S.heading[i] = head[i]; }
+  A.xy_prev[0] = rec[SO_XY_PREV]; A.xy_prev[1] = rec[SO_XY_PREV + 1]; A.psi_prev = rec[SO_PSI_PREV];
+  A.reset_psi = rec[SO_RESET_PSI]; A.waypt[0] = rec[SO_WAYPT]; A.waypt[1] = rec[SO_WAYPT + 1];
+  A.ori[0] = rec[SO_ORI]; A.ori[1] = rec[SO_ORI + 1];
+  A.step_num = rec[SO_STEP_NUM]; A.ep_ret = rec[SO_EP_RET]; A.ep_len = rec[SO_EP_LEN];
+  A.xvel = rec[SO_XVEL]; A.yvel = rec[SO_YVEL];
+  A.head_n = (int)rec[SO_HEAD_N]; A.head_pos = (int)rec[SO_HEAD_POS];
+  if (lane == 0) { S.overflow = 0; S.bad = 0; S.niter_total = 0; S.nls_total = 0; S.nmpr_total = 0; S.nact = 0; }
+  WSYNC();
+}
+TSG_FN void store_env(const EnvScratch& S, const Aux& A, double* rec, double* head, bool need_head, int lane) {
+  LANE_FOR(i, SO_XY_PREV) {
+    double v;
+    if (i < SO_QVEL) v = S.qpos[i];
+    else if (i < SO_WARM) v = S.qvel[i - SO_QVEL];
+    else if (i < SO_CTRL) v = S.warm[i - SO_WARM];
+    else if (i < SO_ACT) v = S.ctrl[i - SO_CTRL];
+    else v = S.act[i - SO_ACT];
+    rec[i] = v;
+  }
+  if (need_head) { LANE_FOR(i, HEADING_SLOTS) head[i] = S.heading[i]; }
+  if (lane == 0) {
+    rec[SO_XY_PREV] = A.xy_prev[0]; rec[SO_XY_PREV + 1] = A.xy_prev[1]; rec[SO_PSI_PREV] = A.psi_prev;
+    rec[SO_RESET_PSI] = A.reset_psi; rec[SO_WAYPT] = A.waypt[0]; rec[SO_WAYPT + 1] = A.waypt[1];
+    rec[SO_ORI] = A.ori[0]; rec[SO_ORI + 1] = A.ori[1];
+    rec[SO_STEP_NUM] = A.step_num; rec[SO_EP_RET] = A.ep_ret; rec[SO_EP_LEN] = A.ep_len;
+    rec[SO_XVEL] = A.xvel; rec[SO_YVEL] = A.yvel;
+    rec[SO_HEAD_N] = (double)A.head_n; rec[SO_HEAD_POS] = (double)A.head_pos;
+  }
+}
+
+struct StepIO {
+  double* state;        // [N][STATE_STRIDE]
+  double* heading;      // [N][HEADING_SLOTS]
+  const double* ctrl64; // [N][6] or null
+  const float* ctrl32;  // [N][6] or null
+  double* obs;          // [N][obs_dim] or null
+  float* obs32;         // [N][obs_dim] or null
+  double* reward;       // [N] or null
+  uint8_t* done;        // [N] or null (terminated | truncated)
+  double* info;         // [N][INFO_DIM] or null
+  double* term_obs;     // [N][obs_dim] or null : observation before an auto reset
+  double* draws;        // [N][NDRAW]: reset draws (in: explicit, out: generated)
+  const uint8_t* mask;  // reset: which envs ; null = all
+  unsigned long long seed;
+  long long env_id_base;
+  int n_envs;
+  int explicit_draws;
+};
+
+TSG_FN void write_obs(const EnvScratch& S, const EnvCfg& c, const StepIO& io, int e, int lane) {
+  if (io.obs) { LANE_FOR(i, c.obs_dim) io.obs[(size_t)e * c.obs_dim + i] = S.obs[i]; }
+  if (io.obs32) { LANE_FOR(i, c.obs_dim) io.obs32[(size_t)e * c.obs_dim + i] = (float)S.obs[i]; }
+}
+
+// the body of the step kernel for env e
+TSG_FN void run_step(EnvScratch& S, const DevModel& m, const EnvCfg& c, const StepIO& io, int e, int lane) {
+  Aux A; StepOut O;
+  bool need_head = (c.task == TASK_TURN || c.task == TASK_AIMING);
+  load_env(S, A, io.state + (size_t)e * STATE_STRIDE, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+  LANE_FOR(i, NACT) S.action[i] = io.ctrl64 ? io.ctrl64[(size_t)e * NACT + i] : (double)io.ctrl32[(size_t)e * NACT + i];
+  WSYNC();
+  env_step(A, O, CTX_ARGS);
+  compute_obs(S, m, c, A, lane);
+  A.ep_len += 1; A.ep_ret += O.reward;
+  int truncated = (c.max_episode_steps > 0 && A.ep_len >= c.max_episode_steps) ? 1 : 0;
+  write_obs(S, c, io, e, lane);
+  if (lane == 0) {
+    if (io.reward) io.reward[e] = O.reward;
+    if (io.done) io.done[e] = (uint8_t)((O.terminated || truncated) ? 1 : 0);
+  }
+  if (io.info) {
+    double* I = io.info + (size_t)e * INFO_DIM;
+    LANE_FOR(i, INFO_DIM) {
+      double v = 0;
+      switch (i) {
+        case IO_REW_FWD: v = O.fwd; break;
+        case IO_REW_CTRL: v = -O.ctrl_cost; break;
+        case IO_REW_SURVIVE: v = O.healthy; break;
+        case IO_X: v = O.xy[0]; break;
+        case IO_Y: v = O.xy[1]; break;
+        case IO_PSI: v = O.psi; break;
+        case IO_XVEL: v = A.xvel; break;
+        case IO_YVEL: v = A.yvel; break;
+        case IO_TERMINATED: v = O.terminated; break;
+        case IO_TRUNCATED: v = truncated; break;
+        case IO_NCON: v = S.nact; break;
+        case IO_NITER: v = S.niter_total; break;
+        case IO_NLS: v = S.nls_total; break;
+        case IO_BARFORCE: v = O.barforce; break;
+        case IO_MAXCFRC: v = O.maxcfrc; break;
+        case IO_WAYPT: v = A.waypt[0]; break;
+        case IO_WAYPT + 1: v = A.waypt[1]; break;
+        case IO_ORI: v = A.ori[0]; break;
+        case IO_ORI + 1: v = A.ori[1]; break;
+        case IO_OVERFLOW: v = S.overflow; break;
+        case IO_BAD: v = S.bad; break;
+        case IO_NMPR: v = S.nmpr_total; break;
+        default: if (i >= IO_TEN && i < IO_TEN + 9) v = S.tlen[i - IO_TEN];
+      }
+      I[i] = v;
+    }
+  }
+  store_env(S, A, io.state + (size_t)e * STATE_STRIDE, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+}
+
+// Philox4x32-10, counter = (env id, reset count), key = seed
+TSG_FN void philox(unsigned long long seed, unsigned long long ctr_lo, unsigned long long ctr_hi, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+TSG_FN double u01(uint32_t a, uint32_t b) {  // 53-bit uniform in [0,1)
+  unsigned long long x = (((unsigned long long)a << 32) | b) >> 11;
+  return (double)x * (1.0 / 9007199254740992.0);
+}
+TSG_FN void make_draws(double* d, unsigned long long seed, unsigned long long env_id, unsigned long long nreset) {
+  double un[12];
+  for (int k = 0; k < 6; k++) {
+    uint32_t r[4];
+    philox(seed, env_id, (nreset << 8) | (unsigned long long)k, r);
+    un[2 * k] = u01(r[0], r[1]); un[2 * k + 1] = u01(r[2], r[3]);
+  }
+  d[0] = un[0]; d[1] = un[1]; d[8] = un[2]; d[9] = un[3];
+  for (int k = 0; k < 3; k++) {  // Box-Muller
+    double u1 = 1.0 - un[4 + 2 * k], u2 = un[5 + 2 * k];
+    double r = sqrt(-2.0 * log(u1));
+    d[2 + 2 * k] = r * cos(2 * PI * u2); d[3 + 2 * k] = r * sin(2 * PI * u2);
+  }
+}
+
+// the body of the reset kernel for env e (mask already checked)
+TSG_FN void run_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, const StepIO& io, int e, int lane) {
+  Aux A;
+  bool need_head = (c.task == TASK_TURN || c.task == TASK_AIMING);
+  double* rec = io.state + (size_t)e * STATE_STRIDE;
+  load_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+  if (io.term_obs && io.obs) { LANE_FOR(i, c.obs_dim) io.term_obs[(size_t)e * c.obs_dim + i] = io.obs[(size_t)e * c.obs_dim + i]; }
+  double nreset = rec[SO_NRESET];
+  if (io.explicit_draws) { LANE_FOR(i, NDRAW) S.draws[i] = io.draws[(size_t)e * NDRAW + i]; }
+  else {
+    if (lane == 0) make_draws(S.draws, io.seed, (unsigned long long)(io.env_id_base + e), (unsigned long long)nreset);
+    WSYNC();
+    if (io.draws) { LANE_FOR(i, NDRAW) io.draws[(size_t)e * NDRAW + i] = S.draws[i]; }
+  }
+  WSYNC();
+  env_reset(S, m, c, A, lane);
+  compute_obs(S, m, c, A, lane);
+  write_obs(S, c, io, e, lane);
+  store_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+  if (lane == 0) rec[SO_NRESET] = nreset + 1;
+}
+
+// mj_forward on the stored state (after tsg_set_state): refresh kinematics bookkeeping and obs
+TSG_FN void run_forward(EnvScratch& S, const DevModel& m, const EnvCfg& c, const StepIO& io, int e, int lane) {
+  Aux A;
+  bool need_head = (c.task == TASK_TURN || c.task == TASK_AIMING);
+  double* rec = io.state + (size_t)e * STATE_STRIDE;
+  load_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+  forward(CTX_ARGS);
+  stage_cfrc(S, m, lane);
+  aux_from_forward(S, A);
+  compute_obs(S, m, c, A, lane);
+  write_obs(S, c, io, e, lane);
+  if (io.info) {
+    double* I = io.info + (size_t)e * INFO_DIM;
+    LANE_FOR(i, INFO_DIM) {
+      double v = 0;
+      if (i >= IO_TEN && i < IO_TEN + 9) v = S.tlen[i - IO_TEN];
+      else if (i == IO_NCON) v = S.nact;
+      else if (i == IO_X) v = A.xy_prev[0];
+      else if (i == IO_Y) v = A.xy_prev[1];
+      else if (i == IO_PSI) v = A.psi_prev;
+      I[i] = v;
+    }
+  }
+  store_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
+}
+
+}  // namespace tsg
