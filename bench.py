@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the tensegrity hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl reference]
+
+A "step" is one env step (frame_skip = 20 substeps + obs/reward/done, in-kernel auto reset) of ALL envs of a
+rank: flat-ground XML, tr_env `straight`, fp64, uniform random ctrl in [-0.45, -0.15] drawn on the device
+before the timed region (BASELINE configs[1] inputs at the per-GPU env count of configs[4]).  Prints ONE JSON
+line (rank 0).  `value` = whole-job env-steps/s with inputs resident in HBM, device-timed (CUDA events on the
+launching stream), max over ranks; `e2e` = the same through the public host API (pinned host ctrl in, host
+obs/reward/done out, copies inside the timed region); `roofline` / `cpu_baseline` per the round contract.
+`--impl reference` times the CPU restatement of the reference path (the oracle; MuJoCo itself is not
+installable here) on all host threads -- rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (whole box, device-timed)"
+UNIT = "env-steps/s"
+CTRL_LO, CTRL_HI = -0.45, -0.15
+L2_BYTES = 126 * 2 ** 20
+
+
+def algorithmic_bytes(obs_dim):
+    """state read + written once (71 doubles each way), ctrl in, obs / reward / done out."""
+    return 2 * 71 * 8 + 6 * 8 + obs_dim * 8 + 8 + 1
+
+
+def flops_per_env_step(ncon, niter_per_sub, frame_skip=20):
+    """SURVEY 8(d) FLOP model (FMA = 2): per substep 3.0k + 0.45k*ncon + n_iter*(1.5k + 0.9k*ncon)."""
+    return frame_skip * (3.0e3 + 0.45e3 * ncon + niter_per_sub * (1.5e3 + 0.9e3 * ncon))
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs (recipe in B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference path on all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.lib().tsgo_max_threads()
+    n_envs = args.ref_envs or 32 * threads
+    b = O.Batch("flat", n_envs, seed=0)
+    b.step(50, lo=0.15, hi=0.15)           # the reset warm-up (50 env steps), untimed, like the GPU arm's reset
+    for _ in range(args.warmup):
+        b.step(1, lo=CTRL_LO, hi=CTRL_HI)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.step(1, lo=CTRL_LO, hi=CTRL_HI)
+    dt = time.perf_counter() - t0
+    b.close()
+    value = n_envs * args.steps / dt
+    sample = "%d envs x %d env-steps (each 20 substeps), flat XML, random ctrl, %d host threads" % (n_envs, args.steps, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "flat_random_ctrl_fp64 (CPU restatement of the reference path; MuJoCo 2.3.7 is not installable here)",
+                   "envs": n_envs, "frame_skip": 20},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_sample(seconds=12.0):
+    from oracle import oracle as O
+    threads = O.lib().tsgo_max_threads()
+    n_envs = 32 * threads
+    b = O.Batch("flat", n_envs, seed=0)
+    b.step(50, lo=0.15, hi=0.15)
+    b.step(2, lo=CTRL_LO, hi=CTRL_HI)
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < seconds:
+        n += b.step(5, lo=CTRL_LO, hi=CTRL_HI)
+    dt = time.perf_counter() - t0
+    b.close()
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs, %d env-steps in %.1f s, flat XML random ctrl, oracle (our CPU restatement, not MuJoCo), "
+                      "%d threads" % (n_envs, n, dt, threads)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=131072, help="envs per GPU (weak scaling)")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--ref-envs", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", default="4096,65536", help="extra env counts timed briefly at N=1 (reported in config)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tensegrity_rl_b200 import TensegrityVecEnv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def timed_run(env, n_envs, steps, warmup, flush):
+        g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        ctrl = CTRL_LO + (CTRL_HI - CTRL_LO) * torch.rand(steps + warmup, n_envs, 6, generator=g, device=dev, dtype=torch.float64)
+        scratch = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if flush else None
+        for k in range(warmup):
+            env.step_tensor(ctrl[k], want_info=False)
+        stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = env.launches
+        barrier()
+        for k in range(steps):
+            if flush:
+                scratch.fill_(k & 255)       # evict L2 between timed iterations (outside the event pair)
+            ev[k][0].record()
+            obs, rew, done = env.step_tensor(ctrl[warmup + k], want_info=(k == steps - 1))
+            ev[k][1].record()
+            stats[0] += rew.sum(); stats[1] += done.sum()
+        if world > 1:                        # the only collective of the path: episode statistics
+            dist.all_reduce(stats)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return ms, env.launches - l0, stats
+
+    env = TensegrityVecEnv(n, xml_file="flat", env="tr_env", device=local_rank, seed=0, env_id_base=rank * n,
+                           auto_reset=True, desired_action="straight")
+    env.reset_tensor()
+    torch.cuda.synchronize()
+    state_bytes = n * (96 * 8 + env.obs_dim * 8 + 6 * 8)
+    flush = state_bytes < 2 * L2_BYTES
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, stats = timed_run(env, n, args.steps, args.warmup, flush)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # per-step solver statistics of the last step (for the FLOP model) and contact overflow / bad-state counters
+    info = env.info
+    ncon, niter, nls = float(info[:, 19].mean()), float(info[:, 20].mean()) / 20, float(info[:, 21].mean()) / 20
+    overflow, bad = float(info[:, 28].sum()), float(info[:, 29].sum())
+    done_frac = float(stats[1].item()) / (world * n * args.steps)
+
+    # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hc = torch.empty(n, 6, dtype=torch.float64).pin_memory()
+        ho = torch.empty(n, env.obs_dim, dtype=torch.float64).pin_memory()
+        hr = torch.empty(n, dtype=torch.float64).pin_memory()
+        hd = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dc = torch.empty(n, 6, dtype=torch.float64, device=dev)
+        gen = torch.Generator(); gen.manual_seed(99 + rank)
+        ksteps = max(3, min(args.steps, 10))
+        hsrc = CTRL_LO + (CTRL_HI - CTRL_LO) * torch.rand(ksteps + 2, n, 6, generator=gen, dtype=torch.float64)
+
+        def host_step(k):
+            hc.copy_(hsrc[k])                            # the caller's actions land in pinned memory
+            dc.copy_(hc, non_blocking=True)              # H2D
+            obs, rew, done = env.step_tensor(dc, want_info=False)
+            ho.copy_(obs, non_blocking=True); hr.copy_(rew, non_blocking=True); hd.copy_(done, non_blocking=True)  # D2H
+            torch.cuda.synchronize()
+        for k in range(2):
+            host_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(ksteps):
+            host_step(2 + k)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * ksteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 6 * 8,
+               "d2h_bytes_per_step": n * (env.obs_dim * 8 + 8 + 1), "steps": ksteps,
+               "api": "TensegrityVecEnv.step_tensor with pinned host ctrl/obs/reward/done copies"}
+
+    sweep = {}
+    if rank == 0 and world == 1 and args.sweep:
+        for s in [int(x) for x in args.sweep.split(",") if x]:
+            if s == n:
+                continue
+            e2 = TensegrityVecEnv(s, xml_file="flat", env="tr_env", device=local_rank, seed=0, auto_reset=True)
+            e2.reset_tensor()
+            m2, _, _ = timed_run(e2, s, 10, 3, True)
+            sweep[str(s)] = s * 10 / (m2 * 1e-3)
+            e2.close()
+
+    if rank == 0:
+        obs_dim = env.obs_dim
+        balg = algorithmic_bytes(obs_dim)
+        kernel_ms = ms_max / args.steps          # one step kernel launch per step (+ a masked reset launch)
+        achieved = balg * n / (kernel_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        fl = flops_per_env_step(ncon, niter)
+        tflops = fl * n / (kernel_ms * 1e-3) / 1e12
+        cfgk = env.kernel_config()
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "flat_random_ctrl_fp64: 3prism_jonathan_steady_side.xml, tr_env straight, ctrl~U[-0.45,-0.15], "
+                                   "%d envs/GPU (BASELINE configs[1] inputs at the configs[4] per-GPU env count)" % n,
+                       "envs_per_gpu": n, "frame_skip": 20, "obs_dim": obs_dim, "auto_reset": True,
+                       "l2": "flush between timed steps" if flush else "state+obs working set %.0f MB > 126 MB L2" % (state_bytes / 2 ** 20),
+                       "done_fraction_per_step": done_frac, "mean_contacts": ncon, "newton_iters_per_substep": niter,
+                       "linesearch_evals_per_substep": nls, "contact_overflow": overflow, "bad_state": bad,
+                       "kernel": cfgk, "sweep_env_steps_per_s": sweep},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "algorithmic_bytes_per_env_step": balg,
+                         "note": "the path is latency/FP64-issue bound, not HBM bound (SURVEY 8d): HBM axis reported for completeness",
+                         "fp64_model": {"flops_per_env_step": fl, "achieved_tflops": tflops, "nominal_peak_tflops": 37.0,
+                                        "frac": tflops / 37.0}},
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(out))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

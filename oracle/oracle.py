@@ -149,6 +149,29 @@ def bench(xml_file, n_envs, n_steps, threads=0, frame_skip=20, warm_steps=0, lo=
     return n, time.perf_counter() - t0, threads, cs.value
 
 
+class Batch:
+    """persistent batch of oracle envs stepped by a pthread pool (CPU arm of bench.py)."""
+
+    def __init__(self, xml_file, n_envs, seed=0):
+        self.mj = MjLike(xml_file)
+        self.L = lib()
+        self.L.tsgo_batch_create.restype = C.c_void_p
+        self.L.tsgo_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong]
+        self.L.tsgo_batch_step.restype = C.c_long
+        self.L.tsgo_batch_step.argtypes = [C.c_void_p, C.c_int, C.c_int, d, d, C.c_int]
+        self.L.tsgo_batch_destroy.argtypes = [C.c_void_p]
+        self.n_envs = n_envs
+        self.b = self.L.tsgo_batch_create(C.addressof(self.mj.model), n_envs, seed)
+
+    def step(self, n_steps=1, frame_skip=20, lo=-0.45, hi=-0.15, threads=0):
+        return self.L.tsgo_batch_step(self.b, n_steps, frame_skip, lo, hi, threads)
+
+    def close(self):
+        if self.b:
+            self.L.tsgo_batch_destroy(self.b)
+            self.b = None
+
+
 def mpr(type1, pos1, mat1, size1, type2, pos2, mat2, size2, tol=1e-6, iters=50):
     L = lib()
     f = lambda a: np.ascontiguousarray(a, np.float64)

@@ -1083,6 +1083,54 @@ int tsgo_max_threads(void) {
   long n = sysconf(_SC_NPROCESSORS_ONLN);
   return n > 0 ? (int)n : 1;
 }
+/* persistent batch of independent envs stepped by a pthread pool (the timed CPU arm of bench.py) */
+typedef struct TsgoBatch {
+  const TsgModel *m; int n_envs; TsgoData *d; unsigned long long *rng;
+  int frame_skip; double lo, hi; int n_steps; int next; pthread_mutex_t mu;
+} TsgoBatch;
+TsgoBatch *tsgo_batch_create(const TsgModel *m, int n_envs, unsigned long long seed) {
+  TsgoBatch *b = (TsgoBatch *)calloc(1, sizeof(TsgoBatch));
+  b->m = m; b->n_envs = n_envs;
+  b->d = (TsgoData *)malloc(sizeof(TsgoData) * (size_t)n_envs);
+  b->rng = (unsigned long long *)malloc(sizeof(unsigned long long) * (size_t)n_envs);
+  for (int e = 0; e < n_envs; e++) { tsgo_reset_data(m, &b->d[e]); b->rng[e] = seed * 1000003ULL + (unsigned long long)e; }
+  pthread_mutex_init(&b->mu, 0);
+  return b;
+}
+void tsgo_batch_destroy(TsgoBatch *b) { if (b) { free(b->d); free(b->rng); free(b); } }
+static void *batch_worker(void *arg) {
+  TsgoBatch *b = (TsgoBatch *)arg;
+  for (;;) {
+    pthread_mutex_lock(&b->mu);
+    int e = b->next++;
+    pthread_mutex_unlock(&b->mu);
+    if (e >= b->n_envs) break;
+    TsgoData *d = &b->d[e];
+    for (int st = 0; st < b->n_steps; st++) {
+      for (int i = 0; i < TSG_NACT; i++) {
+        double u = (double)(splitmix(&b->rng[e]) >> 11) * (1.0 / 9007199254740992.0);
+        d->ctrl[i] = b->lo + (b->hi - b->lo) * u;
+      }
+      tsgo_step(b->m, d, b->frame_skip);
+      tsgo_rne_post_constraint(b->m, d);
+    }
+  }
+  return 0;
+}
+/* n_steps env-steps (frame_skip substeps + mj_rnePostConstraint each) for every env, uniform random ctrl */
+long tsgo_batch_step(TsgoBatch *b, int n_steps, int frame_skip, double lo, double hi, int n_threads) {
+  if (n_threads <= 0) n_threads = tsgo_max_threads();
+  if (n_threads > 256) n_threads = 256;
+  b->n_steps = n_steps; b->frame_skip = frame_skip; b->lo = lo; b->hi = hi; b->next = 0;
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; t++) pthread_create(&th[t], 0, batch_worker, b);
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], 0);
+  return (long)b->n_envs * n_steps;
+}
+void tsgo_batch_get(const TsgoBatch *b, int e, double *qpos, double *qvel) {
+  memcpy(qpos, b->d[e].qpos, sizeof(double) * TSG_NQ); memcpy(qvel, b->d[e].qvel, sizeof(double) * TSG_NV);
+}
+
 typedef struct {
   const TsgModel *m; int n_envs, n_steps, frame_skip, warm_steps; double lo, hi; unsigned long long seed;
   int next; pthread_mutex_t mu; double checksum; long total;

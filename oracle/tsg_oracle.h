@@ -125,11 +125,17 @@ int tsgo_mpr(int type1, const double *pos1, const double *mat1, const double *si
              double tolerance, int max_iterations, double *depth, double *dir, double *pos);
 
 /* CPU baseline: step n_envs independent envs n_steps env-steps (frame_skip substeps each)
- * with uniform random ctrl in [lo,hi], OpenMP over envs.  Returns env-steps done. */
+ * with uniform random ctrl in [lo,hi], a pthread pool over envs.  Returns env-steps done. */
 long tsgo_bench(const TsgModel *m, int n_envs, int n_steps, int frame_skip, int warm_steps,
                 double ctrl_lo, double ctrl_hi, unsigned long long seed, int n_threads,
                 double *out_checksum);
 int tsgo_max_threads(void);
+/* persistent batch of envs stepped by a pthread pool (bench.py CPU arm) */
+typedef struct TsgoBatch TsgoBatch;
+TsgoBatch *tsgo_batch_create(const TsgModel *m, int n_envs, unsigned long long seed);
+void tsgo_batch_destroy(TsgoBatch *b);
+long tsgo_batch_step(TsgoBatch *b, int n_steps, int frame_skip, double lo, double hi, int n_threads);
+void tsgo_batch_get(const TsgoBatch *b, int e, double *qpos, double *qvel);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+"""CPU check of the CUDA SOURCE's lane logic: tsg_core.cuh / tsg_env.cuh compiled as a serial one-warp
+emulator (tests/emul) against the oracle.  The GPU twin of these tests is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from emul import emul as E
+from oracle.envs import OracleEnv
+
+
+def _copy_state(mj, em):
+    em.rec[0:21] = mj.qpos
+    em.rec[21:39] = mj.qvel
+    em.rec[39:57] = mj.qacc_warmstart
+    em.rec[63:69] = mj.act
+
+
+@pytest.mark.parametrize("model,lo,hi", [("flat", -0.45, -0.15), ("flat", -0.45, 0.15), ("uneven", -0.45, 0.15)])
+def test_single_step_state_parity(oracle, model, lo, hi):
+    """one env step (20 substeps) from identical (qpos, qvel, act, warmstart, ctrl): 1e-9 relative."""
+    mj, em = oracle.MjLike(model), E.Emul(model)
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for st in range(60):
+        ctrl = rng.uniform(lo, hi, 6)
+        _copy_state(mj, em)
+        mj.ctrl[:] = ctrl
+        mj.step(20)
+        mj.rne_post_constraint()
+        ten, cfrc, stats = em.mj_step(ctrl, 20)
+        assert stats[4] == 0 and stats[5] == 0
+        for a, b in ((em.qpos, mj.qpos), (em.qvel, mj.qvel), (ten, mj.ten_length)):
+            worst = max(worst, np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+        assert np.abs(cfrc - mj.cfrc_ext).max() <= 1e-7 * max(1.0, np.abs(mj.cfrc_ext).max())
+    assert worst < 1e-9, worst
+
+
+def test_conservative_prefilter_matches_unfiltered_oracle(oracle):
+    """the CUDA source filters bar-bar pairs with an analytic capsule bound before MPR; the oracle runs MPR on
+    every pair that passes MuJoCo's bounding-sphere test.  Squeeze the bars together and compare."""
+    mj, em = oracle.MjLike("flat"), E.Emul("flat")
+    rng = np.random.default_rng(7)
+    nbar = 0
+    for st in range(80):
+        ctrl = rng.uniform(-0.45, -0.35, 6)
+        _copy_state(mj, em)
+        mj.ctrl[:] = ctrl
+        mj.step(5)
+        ten, cfrc, stats = em.mj_step(ctrl, 5)
+        nbar += sum(1 for c in mj.contacts() if c.geom1 != 0 and c.efc_address >= 0)
+        assert np.abs(em.qvel - mj.qvel).max() <= 1e-9 * max(1.0, np.abs(mj.qvel).max())
+        assert stats[0] == mj.nefc // 6
+    assert nbar > 20  # the scenario really exercises bar-bar contact
+
+
+CASES = [("flat", "tr_env", "straight"), ("flat", "tr_env", "turn"), ("flat", "tr_env", "aiming"),
+         ("flat", "tr_env", "tracking"), ("flat", "tr_env", "vel_track"), ("flat", "tensegrity_env", "straight"),
+         ("flat", "tensegrity_env", "turn"), ("uneven", "tensegrity_env", "straight")]
+
+
+@pytest.mark.parametrize("xml,kind,task", CASES)
+def test_env_semantics_parity(xml, kind, task):
+    rng = np.random.default_rng(11)
+    oe = OracleEnv(xml, kind, desired_action=task)
+    em = E.Emul(xml, env_kind=kind, desired_action=task)
+    draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
+    o1, o2 = oe.reset(draws), em.reset(draws)
+    assert o1.shape == o2.shape == (oe.cfg.obs_dim,)
+    assert np.abs(o1 - o2).max() < 1e-7
+    lo, hi = (-0.45, -0.15) if kind == "tensegrity_env" else (-0.45, 0.15)
+    for st in range(12):
+        a = rng.uniform(lo, hi, 6)
+        ob1, r1, t1, tr1, i1 = oe.step(a)
+        ob2, r2, d2, info = em.step(a)
+        assert np.abs(ob1 - ob2).max() < 1e-7
+        assert abs(r1 - r2) <= 1e-7 * max(1.0, abs(r1))
+        assert (t1 or tr1) == d2
+        assert info[3] == pytest.approx(i1["x_position"], abs=1e-8)
+        assert info[5] == pytest.approx(i1["psi"], abs=1e-7)
+
+
+def test_time_limit_and_step_cap():
+    em = E.Emul("flat", env_kind="tr_env", desired_action="tracking", max_episode_steps=3)
+    em.reset(np.array([0.1, 0.2, 0, 0, 0, 0, 0, 0, 0.5, 0.5]))
+    dones = [em.step(np.full(6, 0.1))[2] for _ in range(3)]
+    assert dones == [False, False, True]  # TimeLimit.truncated on the 3rd step
+
+
+def test_philox_draws_are_keyed_by_env_and_reset_count():
+    import ctypes as C
+    L = E.lib()
+    def draws(seed, env, n):
+        d = np.zeros(10)
+        L.emul_make_draws(E.P(d), C.c_ulonglong(seed), C.c_ulonglong(env), C.c_ulonglong(n))
+        return d
+    a, b, c, d = draws(1, 5, 0), draws(1, 5, 0), draws(1, 6, 0), draws(1, 5, 1)
+    assert np.array_equal(a, b) and not np.array_equal(a, c) and not np.array_equal(a, d)
+    u = np.array([draws(3, e, 0) for e in range(4000)])
+    assert (u[:, [0, 1, 8, 9]] >= 0).all() and (u[:, [0, 1, 8, 9]] < 1).all()
+    assert abs(u[:, [0, 1, 8, 9]].mean() - 0.5) < 0.02
+    assert abs(u[:, 2:8].mean()) < 0.03 and abs(u[:, 2:8].std() - 1) < 0.03

