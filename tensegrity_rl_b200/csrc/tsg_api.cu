@@ -10,8 +10,11 @@
 
 using namespace tsg;
 
+#ifndef TSG_MIN_CTAS
+#define TSG_MIN_CTAS 4  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
+#endif
 #ifndef TSG_WARPS
-#define TSG_WARPS 3  // warps (= envs) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
+#define TSG_WARPS 4  // warps (= envs in flight) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
 #endif
 
 static_assert(STATE_STRIDE == TSG_STATE_STRIDE && INFO_DIM == TSG_INFO_DIM && NDRAW == TSG_NDRAW, "ABI constants");
@@ -22,12 +25,15 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 
 constexpr size_t SMEM_TOTAL = SMEM_MODEL + SMEM_CFG + TSG_WARPS * SMEM_SCRATCH;
 
-// One warp per env.  The model constants are staged once per CTA in shared memory (lane-indexed
-// reads of them would serialise in the constant cache); after that warps never synchronise with
-// each other.
+// One warp per env, persistent CTAs: the grid is sized to fill the machine once (SMs x resident CTAs) and every
+// warp pulls env indices from a global counter until the batch is done, so envs of different cost (contact
+// count, Newton iterations, resets) balance dynamically and the model constants are staged once per CTA in
+// shared memory (lane-indexed reads of them would serialise in the constant cache).  Warps never synchronise
+// with each other after that.
 template <int MODE>
-__global__ void __launch_bounds__(TSG_WARPS * 32) tsg_env_kernel(const DevModel* __restrict__ gm,
-                                                                  const EnvCfg* __restrict__ gc, StepIO io) {
+__global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(const DevModel* __restrict__ gm,
+                                                                  const EnvCfg* __restrict__ gc, StepIO io,
+                                                                  Con* __restrict__ spill_base, int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char tsg_smem[];
   unsigned char* smem = tsg_smem;
   {
@@ -42,12 +48,20 @@ __global__ void __launch_bounds__(TSG_WARPS * 32) tsg_env_kernel(const DevModel*
   const DevModel& m = *reinterpret_cast<const DevModel*>(smem);
   const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(smem + SMEM_MODEL);
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int e = blockIdx.x * TSG_WARPS + warp;
-  if (e >= io.n_envs) return;
   EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
-  if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
-  else if (MODE == MODE_RESET) { if (io.mask && !io.mask[e]) return; run_reset(S, m, c, io, e, lane); }
-  else run_forward(S, m, c, io, e, lane);
+  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * TSG_WARPS + warp) * (MAXC - MAXC_S);
+  __syncwarp();
+  for (;;) {
+    int e = 0;
+    if (lane == 0) e = atomicAdd(counter, 1);
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (e >= io.n_envs) break;
+    if (MODE == MODE_RESET && io.mask && !io.mask[e]) continue;
+    if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
+    else if (MODE == MODE_RESET) run_reset(S, m, c, io, e, lane);
+    else run_forward(S, m, c, io, e, lane);
+    __syncwarp();
+  }
 }
 
 // record <-> separate arrays (tsg_get_state / tsg_set_state)
@@ -91,6 +105,8 @@ struct TsgHandle {
   // staging for the host-buffer entry points
   double *d_ctrl, *d_obs, *d_reward, *d_info, *d_termobs, *d_tmp;
   uint8_t* d_mask;
+  Con* d_spill; int* d_counter;
+  int grid[3];
   cudaStream_t own_stream;
 };
 
@@ -111,15 +127,21 @@ int tsg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 
 template <int MODE>
 static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
-  static bool attr_done[3] = {false, false, false};
-  if (!attr_done[MODE]) {
-    CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    attr_done[MODE] = true;
-  }
-  int grid = (h->n_envs + TSG_WARPS - 1) / TSG_WARPS;
-  tsg_env_kernel<MODE><<<grid, TSG_WARPS * 32, SMEM_TOTAL, s>>>(h->d_model, h->d_cfg, io);
+  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
+  tsg_env_kernel<MODE><<<h->grid[MODE], TSG_WARPS * 32, SMEM_TOTAL, s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
   CK(cudaGetLastError());
   h->launches++;
+  return 0;
+}
+template <int MODE>
+static int setup_kernel(TsgHandle* h, int num_sms, int* max_grid) {
+  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE>, TSG_WARPS * 32, SMEM_TOTAL));
+  if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
+  int need = (h->n_envs + TSG_WARPS - 1) / TSG_WARPS, full = num_sms * per_sm;
+  h->grid[MODE] = need < full ? need : full;
+  if (h->grid[MODE] > *max_grid) *max_grid = h->grid[MODE];
   return 0;
 }
 
@@ -160,6 +182,11 @@ int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int d
   CK(cudaMemset(h->d_heading, 0, n * HEADING_SLOTS * sizeof(double)));
   CK(cudaMemset(h->d_draws, 0, n * NDRAW * sizeof(double)));
   CK(cudaMemset(h->d_done, 0, n));
+  int max_grid = 0;
+  if (setup_kernel<MODE_STEP>(h, prop.multiProcessorCount, &max_grid) || setup_kernel<MODE_RESET>(h, prop.multiProcessorCount, &max_grid) ||
+      setup_kernel<MODE_FORWARD>(h, prop.multiProcessorCount, &max_grid)) { tsg_destroy(h); return -2; }
+  CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_WARPS * (MAXC - MAXC_S) * sizeof(Con)));
+  CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   tsg_init_records_kernel<<<(n_envs + 127) / 128, 128>>>(h->d_state, n_envs, h->d_model);
   CK(cudaGetLastError());
@@ -172,7 +199,7 @@ int tsg_destroy(TsgHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
-                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask};
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

@@ -24,6 +24,7 @@
 #define TSG_DEVICE 1
 #define TSG_FN __device__ __forceinline__
 #define TSG_FN_NOINLINE __device__ __noinline__
+#define TSG_UNROLL1 _Pragma("unroll 1")
 #define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
 #define LANE_FOR_ALL(i, n) for (int i##_b = 0, i = lane; i##_b < (n); i##_b += 32, i += 32)
 #define WSYNC() __syncwarp()
@@ -31,7 +32,12 @@
 #define TSG_DEVICE 0
 #define TSG_FN static inline
 #define TSG_FN_NOINLINE static
+#define TSG_UNROLL1
+#ifdef TSG_EMUL_REVERSE  // second emulator build: items of a phase in reverse order, to expose intra-phase hazards
+#define LANE_FOR(i, n) for (int i = (n) - 1; i >= 0; --i)
+#else
 #define LANE_FOR(i, n) for (int i = 0; i < (n); ++i)
+#endif
 #define LANE_FOR_ALL(i, n) for (int i = 0; i < (n); ++i)
 #define WSYNC() ((void)0)
 #endif
@@ -39,9 +45,10 @@
 namespace tsg {
 
 constexpr int NBAR = 3, NGEOM = 15, NTEN = 9, NEND = 18, NACT = 6, NQ = 21, NV = 18;
-constexpr int MAXC = 12;        // contact slots per env in shared memory
+constexpr int MAXC_S = 6;       // contact slots per env in shared memory
+constexpr int MAXC = 32;        // total contact slots per env (slots >= MAXC_S spill to a per-warp global area)
 constexpr int MAXCAND = 64;     // narrow-phase candidates per collision pass
-constexpr int HS = 19;          // padded row stride of the Hessian
+constexpr int NTRI = NV * (NV + 1) / 2;  // packed lower triangle of the Hessian
 constexpr double MINVAL = 1e-15, MAXVAL = 1e10, MINIMP = 0.0001, MAXIMP = 0.9999;
 constexpr double CCD_EPS = 2.220446049250313e-16;
 constexpr int GEOM_SPHERE = 2, GEOM_CYL = 5;
@@ -88,11 +95,14 @@ struct DevModel {
   double dynprm0, gain, bias[3], ctrlrange[2], forcerange[2];
   // contact
   double K, B, solimp[5], mu, fr[5], dscale[6], fscale[6];
+  double wtab[2][6];
+  double inv_mu2;     // 1 / (mu^2 (1 + mu^2))  // Hessian row weights per zone: bottom = dscale, middle = (0, fr^2)
   // floor
   int floor_type, nrow, ncol, pad2;
   double fpos[3], fnormal[3], hsize[4];
   const float* hdata;
   double qpos0[NQ];
+  unsigned char tri_i[NTRI + 5], tri_j[NTRI + 5];  // packed-triangle index -> (row, col)
 };
 
 struct EnvCfg {
@@ -107,13 +117,17 @@ struct EnvCfg {
 };
 
 struct Con {
-  double J[2][6][6];  // [side][row][dof of that side's bar], sign applied
+  // Jacobian of the 6 contact rows, per side (side 0 = body b1, side 1 = body b2), sign applied.
+  // translational row a: linear part = sgn * frame[a], angular part = Jt[side][a]; rotational row 3+a: angular Jr[side][a]
+  double Jt[2][3][3];
+  double Jr[2][3][3];
   double frame[9];
   double pos[3];
-  double aref[6], jar[6], jv[6], force[6], w[6];
+  double aref[6];  // after the initial residual is built this holds jv = J * search
+  double jar[6], force[6];
   double bvec[2][6];
   double su[6];
-  double dist, D0, ca, cb;
+  double dist, D0, wcoef, ca, cb;
   double U0, V0, UU, UV, VV, q0, q1, q2;
   int b1, b2;  // bar index 0..2, or -1 for the world
   int zone, active;
@@ -122,38 +136,35 @@ struct Con {
 struct Scratch {
   // env state carried across substeps
   double qpos[NQ], qvel[NV], warm[NV], ctrl[NACT], act[NACT];
-  // position stage
+  // position stage (kept for the epilogue: stale body positions, end-cap centres)
   double xstale[9];
   double xmat[27];
-  double site[NEND * 3];
-  double gpos[NGEOM * 3];
+  double sph[18];
   double tlen[NTEN], tdir[NTEN * 3], tJw[NEND * 3];
   // velocity / force stage
-  double tvel[NTEN], tfrc[NTEN], tB[NTEN], actfrc[NACT], actdot[NACT];
+  double tfrc[NTEN], tB[NTEN], actdot[NACT];
   double fsm[NV], asmooth[NV], fcon[NV];
-  double Dblk[NBAR][21];
-  // solver
+  // solver vectors
   double qacc[NV], grad[NV], search[NV], rhs[NV], dinv[NV];
-  double H[NV * HS];
-  double lsacc[2][MAXC][3];
-  double red[32];
-  double cfrc[4][6];
-  Con con[MAXC];
+  double qG[3], lsr[3], gauss;
+  // time-multiplexed region: collision temporaries -> Hessian -> line-search sums -> post-solve data
+  union {
+    struct { int cand[MAXCAND]; int hf_cell[NGEOM][4]; double hf_zmin[NGEOM]; } col;
+    struct { double H[NTRI]; } hes;
+    struct { double acc[MAXC][3]; } ls;
+    struct { double Dblk[NBAR][21]; double cfrc[4][6]; double obs[64]; } post;
+  } u;
+  Con con[MAXC_S];
+  Con* spill;  // global memory, MAXC - MAXC_S slots owned by this warp
   int order[MAXC];
-  int cand[MAXCAND];
-  int hf_cell[NGEOM][4];
-  double hf_zmin[NGEOM];
   int nact, nslot, overflow, bad;
-  int niter_total, nls_total, nmpr_total, pad;
+  int niter_total, nls_total, nmpr_total, ls_evals;
 };
 
 struct EnvScratch : Scratch {
-  double heading[HEADING_SLOTS];
-  double obs[64];
   double action[NACT];
   double draws[NDRAW + 2];
 };
-
 
 // ---- shared-memory context.  Heavy stages are compiled ONCE as __noinline__ functions; on the device
 // they re-derive their context from the dynamic shared-memory base so that the compiler keeps LDS/STS
@@ -177,7 +188,38 @@ constexpr size_t SMEM_SCRATCH = align16(sizeof(EnvScratch));
 #define CTX_BIND (void)c;
 #endif
 
+TSG_FN Con& con_at(Scratch& S, int slot) { return slot < MAXC_S ? S.con[slot] : S.spill[slot - MAXC_S]; }
+TSG_FN const Con& con_at(const Scratch& S, int slot) { return slot < MAXC_S ? S.con[slot] : S.spill[slot - MAXC_S]; }
+// J element (row r, dof k of the side's bar) and row . 6-vector products on the compressed storage
+TSG_FN double Jel(const Con& c, int side, int r, int k) {
+  if (r < 3) return k < 3 ? (side ? c.frame[3 * r + k] : -c.frame[3 * r + k]) : c.Jt[side][r][k - 3];
+  return k < 3 ? 0.0 : c.Jr[side][r - 3][k - 3];
+}
+TSG_FN double Jrow_dot(const Con& c, int side, int r, const double* v6) {
+  if (r < 3) {
+    const double* f = c.frame + 3 * r; const double* a = c.Jt[side][r];
+    double lin = f[0] * v6[0] + f[1] * v6[1] + f[2] * v6[2];
+    return (side ? lin : -lin) + a[0] * v6[3] + a[1] * v6[4] + a[2] * v6[5];
+  }
+  const double* a = c.Jr[side][r - 3];
+  return a[0] * v6[3] + a[1] * v6[4] + a[2] * v6[5];
+}
+TSG_FN double Jrow_dot_all(const Con& c, int r, const double* v18) {
+  double v = Jrow_dot(c, 1, r, v18 + 6 * c.b2);
+  if (c.b1 >= 0) v += Jrow_dot(c, 0, r, v18 + 6 * c.b1);
+  return v;
+}
+
 // ------------------------------------------------------------------ small math
+// The kernel is instruction-fetch bound (ncu: stall_no_instruction dominates), so the long IEEE fp64 sqrt /
+// divide sequences exist ONCE as out-of-line functions instead of being expanded at every use.
+TSG_FN_NOINLINE double tsg_sqrt(double x) { return sqrt(x); }
+TSG_FN_NOINLINE double tsg_div(double a, double b) { return a / b; }
+#if TSG_DEVICE
+TSG_FN double tsg_rcp(double x) { return __drcp_rn(x); }  // correctly rounded, == 1.0 / x
+#else
+TSG_FN double tsg_rcp(double x) { return 1.0 / x; }
+#endif
 TSG_FN double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 TSG_FN void cross3(double* r, const double* a, const double* b) {
   double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -189,9 +231,9 @@ TSG_FN void copy3(double* r, const double* a) { r[0] = a[0]; r[1] = a[1]; r[2] =
 TSG_FN void scl3(double* r, const double* a, double s) { r[0] = a[0] * s; r[1] = a[1] * s; r[2] = a[2] * s; }
 TSG_FN void addscl3(double* r, const double* a, double s) { r[0] += a[0] * s; r[1] += a[1] * s; r[2] += a[2] * s; }
 TSG_FN double normalize3(double* a) {
-  double n = sqrt(dot3(a, a));
+  double n = tsg_sqrt(dot3(a, a));
   if (n < MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; }
-  else { double s = 1 / n; a[0] *= s; a[1] *= s; a[2] *= s; }
+  else { double s = tsg_div(1.0, n); a[0] *= s; a[1] *= s; a[2] *= s; }
   return n;
 }
 TSG_FN void mulMV(double* r, const double* R, const double* v) {
@@ -216,9 +258,9 @@ TSG_FN void quat2mat(double* R, const double* q) {
   R[6] = 2 * (q13 - q02); R[7] = 2 * (q23 + q01);
 }
 TSG_FN void normalize4(double* q) {
-  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double n = tsg_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
-  else if (fabs(n - 1) > MINVAL) { double s = 1 / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+  else if (fabs(n - 1) > MINVAL) { double s = tsg_div(1.0, n); q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
 }
 TSG_FN bool is_bad(double x) { return !(x <= MAXVAL && x >= -MAXVAL); }
 TSG_FN double clampd(double x, double lo, double hi) { return fmin(hi, fmax(lo, x)); }
@@ -245,6 +287,12 @@ TSG_FN int scan_slot(int v, int& total, int lane) {
 }
 
 // ------------------------------------------------------------------ kinematics + tendons
+TSG_FN void geom_center(const Scratch& S, const DevModel& m, int g, double* out) {
+  int b = g / 5;
+  double v[3];
+  mulMV(v, S.xmat + 9 * b, m.gpos[g]);
+  add3(out, S.qpos + 7 * b, v);
+}
 TSG_FN void stage_position(Scratch& S, const DevModel& m, int lane) {
   LANE_FOR(b, NBAR) {
     double* q = S.qpos + 7 * b;
@@ -253,27 +301,25 @@ TSG_FN void stage_position(Scratch& S, const DevModel& m, int lane) {
     copy3(S.xstale + 3 * b, q);
   }
   WSYNC();
-  LANE_FOR(i, NEND + NGEOM) {
-    int b; const double* loc; double* out;
-    if (i < NEND) { b = m.tbody[i]; loc = m.tsite[i]; out = S.site + 3 * i; }
-    else { int g = i - NEND; b = g / 5; loc = m.gpos[g]; out = S.gpos + 3 * g; }
-    double v[3];
-    mulMV(v, S.xmat + 9 * b, loc);
-    add3(out, S.qpos + 7 * b, v);
-  }
-  WSYNC();
+  LANE_FOR(i, 6) geom_center(S, m, 5 * (i / 2) + 1 + (i % 2), S.sph + 3 * i);  // end-cap centres s0..s5
 }
 
 TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
   LANE_FOR(t, NTEN) {
-    double dir[3], w[2][3];
-    sub3(dir, S.site + 3 * (2 * t + 1), S.site + 3 * (2 * t));
+    double dir[3], w[2][3], p[2][3];
+    for (int e = 0; e < 2; e++) {
+      int end = 2 * t + e, b = m.tbody[end];
+      double v[3];
+      mulMV(v, S.xmat + 9 * b, m.tsite[end]);
+      add3(p[e], S.qpos + 7 * b, v);
+    }
+    sub3(dir, p[1], p[0]);
     double len = normalize3(dir);
     double vel = 0;
     for (int e = 0; e < 2; e++) {
       int end = 2 * t + e, b = m.tbody[end];
       double r[3], c[3];
-      sub3(r, S.site + 3 * end, S.qpos + 7 * b);
+      sub3(r, p[e], S.qpos + 7 * b);
       cross3(c, r, dir);
       mulMTV(w[e], S.xmat + 9 * b, c);
       copy3(S.tJw + 3 * end, w[e]);
@@ -281,7 +327,7 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
       vel += s * (dot3(dir, S.qvel + 6 * b) + dot3(w[e], S.qvel + 6 * b + 3));
     }
     copy3(S.tdir + 3 * t, dir);
-    S.tlen[t] = len; S.tvel[t] = vel;
+    S.tlen[t] = len;
     double frc = 0, Bt = -m.tdamp[t];
     if (m.tk[t] > 0) {
       if (len > m.tls[t][1]) frc = m.tk[t] * (m.tls[t][1] - len);
@@ -292,7 +338,7 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
     if (a >= 0) {
       double ctrl = S.ctrl[a], input;
       if (m.ctrllimited) ctrl = clampd(ctrl, m.ctrlrange[0], m.ctrlrange[1]);
-      if (m.dyntype) { S.actdot[a] = (ctrl - S.act[a]) / fmax(MINVAL, m.dynprm0); input = S.act[a]; }
+      if (m.dyntype) { S.actdot[a] = tsg_div(ctrl - S.act[a], fmax(MINVAL, m.dynprm0)); input = S.act[a]; }
       else { S.actdot[a] = 0; input = ctrl; }
       double f = m.gain * input + m.bias[0] + m.bias[1] * len + m.bias[2] * vel;
       bool clamped = false;
@@ -300,7 +346,6 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
         clamped = (f <= m.forcerange[0] || f >= m.forcerange[1]);
         f = clampd(f, m.forcerange[0], m.forcerange[1]);
       }
-      S.actfrc[a] = f;
       frc += f;
       if (m.bias[2] != 0 && ((m.flags & 1u) || !clamped)) Bt += m.bias[2];
     }
@@ -309,40 +354,42 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
   WSYNC();
 }
 
-// qfrc_smooth / qacc_smooth (items 0..17) and the per-bar damping-derivative blocks (items 18..80)
+// qfrc_smooth / qacc_smooth
 TSG_FN void stage_smooth(Scratch& S, const DevModel& m, int lane) {
-  LANE_FOR(i, NV + 63) {
-    if (i < NV) {
-      int b = i / 6, j = i % 6;
-      double f = 0;
-      for (int n = 0; n < m.nends[b]; n++) {
-        int end = m.ends[b][n], t = end >> 1;
-        double s = (end & 1) ? 1.0 : -1.0;
-        double Jv = j < 3 ? S.tdir[3 * t + j] : S.tJw[3 * end + j - 3];
-        f += s * S.tfrc[t] * Jv;
-      }
-      double bias;
-      if (j < 3) bias = -m.M[i] * m.grav[j];
-      else {
-        const double* w = S.qvel + 6 * b + 3; const double* I = m.inertia[b];
-        int k = j - 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-        bias = w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]);
-      }
-      S.fsm[i] = f - bias;
-      S.asmooth[i] = (f - bias) * m.invM[i];
-    } else {
-      int idx = i - NV, b = idx / 21, tri = idx % 21;
-      int r = 0; while ((r + 1) * (r + 2) / 2 <= tri) r++;
-      int c = tri - r * (r + 1) / 2;
-      double v = 0;
-      for (int n = 0; n < m.nends[b]; n++) {
-        int end = m.ends[b][n], t = end >> 1;
-        double Jr = r < 3 ? S.tdir[3 * t + r] : S.tJw[3 * end + r - 3];
-        double Jc = c < 3 ? S.tdir[3 * t + c] : S.tJw[3 * end + c - 3];
-        v += S.tB[t] * Jr * Jc;
-      }
-      S.Dblk[b][tri] = v;
+  LANE_FOR(i, NV) {
+    int b = i / 6, j = i % 6;
+    double f = 0;
+    for (int n = 0; n < m.nends[b]; n++) {
+      int end = m.ends[b][n], t = end >> 1;
+      double s = (end & 1) ? 1.0 : -1.0;
+      double Jv = j < 3 ? S.tdir[3 * t + j] : S.tJw[3 * end + j - 3];
+      f += s * S.tfrc[t] * Jv;
     }
+    double bias;
+    if (j < 3) bias = -m.M[i] * m.grav[j];
+    else {
+      const double* w = S.qvel + 6 * b + 3; const double* I = m.inertia[b];
+      int k = j - 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+      bias = w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]);
+    }
+    S.fsm[i] = f - bias;
+    S.asmooth[i] = (f - bias) * m.invM[i];
+  }
+  WSYNC();
+}
+// per-bar blocks of d(passive + actuator force)/d(qvel) (implicitfast), computed after the solver
+TSG_FN void stage_damping_blocks(Scratch& S, const DevModel& m, int lane) {
+  LANE_FOR(idx, 63) {
+    int b = idx / 21, tri = idx % 21;
+    int r = m.tri_i[tri], c = m.tri_j[tri];
+    double v = 0;
+    for (int n = 0; n < m.nends[b]; n++) {
+      int end = m.ends[b][n], t = end >> 1;
+      double Jr = r < 3 ? S.tdir[3 * t + r] : S.tJw[3 * end + r - 3];
+      double Jc = c < 3 ? S.tdir[3 * t + c] : S.tJw[3 * end + c - 3];
+      v += S.tB[t] * Jr * Jc;
+    }
+    S.u.post.Dblk[b][tri] = v;
   }
   WSYNC();
 }
@@ -359,7 +406,7 @@ TSG_FN bool ccd_eq(double a_, double b_) {
   return (b > a) ? (ab < CCD_EPS * b) : (ab < CCD_EPS * a);
 }
 TSG_FN bool ccd_vec_is_origin(const double* a) { return ccd_eq(a[0], 0) && ccd_eq(a[1], 0) && ccd_eq(a[2], 0); }
-TSG_FN void ccd_normalize(double* v) { double s = 1.0 / sqrt(dot3(v, v)); v[0] *= s; v[1] *= s; v[2] *= s; }
+TSG_FN void ccd_normalize(double* v) { double s = tsg_div(1.0, tsg_sqrt(dot3(v, v))); v[0] *= s; v[1] *= s; v[2] *= s; }
 
 TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
   if (o.type == 100) {
@@ -372,8 +419,8 @@ TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
   mulMTV(ld, o.mat, dir);
   if (o.type == GEOM_SPHERE) scl3(res, ld, o.size[0]);
   else {
-    double tmp = sqrt(ld[0] * ld[0] + ld[1] * ld[1]);
-    if (tmp > MINVAL) { res[0] = ld[0] / tmp * o.size[0]; res[1] = ld[1] / tmp * o.size[0]; }
+    double tmp = tsg_sqrt(ld[0] * ld[0] + ld[1] * ld[1]);
+    if (tmp > MINVAL) { double it = tsg_div(o.size[0], tmp); res[0] = ld[0] * it; res[1] = ld[1] * it; }
     else res[0] = res[1] = 0;
     res[2] = (ld[2] > 0 ? 1.0 : (ld[2] < 0 ? -1.0 : 0.0)) * o.size[1];
   }
@@ -387,7 +434,7 @@ TSG_FN void obj_center(const CObj& o, double* c) {
     c[0] /= 6; c[1] /= 6; c[2] /= 6;
   } else copy3(c, o.pos);
 }
-TSG_FN void mink_support(const CObj& o1, const CObj& o2, const double* dir, Supp& s) {
+TSG_FN_NOINLINE void mink_support(const CObj& o1, const CObj& o2, const double* dir, Supp& s) {
   double nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
   obj_support(o1, dir, s.v1);
   obj_support(o2, nd, v2);
@@ -425,7 +472,7 @@ TSG_FN double tri_dist2_origin(const double* x0, const double* B, const double* 
   double v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
   double s, t, dist, dd = w * v - r * r;
   if (ccd_is_zero(dd)) s = t = -1;
-  else { s = (q * r - w * p) / dd; t = (-s * r - q) / w; }
+  else { s = tsg_div(q * r - w * p, dd); t = tsg_div(-s * r - q, w); }
   if ((ccd_is_zero(s) || s > 0) && (ccd_eq(s, 1.0) || s < 1) && (ccd_is_zero(t) || t > 0) &&
       (ccd_eq(t, 1.0) || t < 1) && (ccd_eq(t + s, 1.0) || t + s < 1)) {
     scl3(d1, d1, s); scl3(d2, d2, t);
@@ -461,7 +508,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
     double v2[3];
     sub3(v2, p[1].v1, p[1].v);
     add3(pos_out, p[1].v1, v2); scl3(pos_out, pos_out, 0.5);
-    copy3(dir_out, p[1].v); *depth = sqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
+    copy3(dir_out, p[1].v); *depth = tsg_sqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
     return true;
   }
   ccd_normalize(dir);
@@ -502,7 +549,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
     mink_support(o1, o2, dir, v4);
     if (portal_reach_tol(p, v4, dir, tol) || it > max_iter) {
       double pdir[3];
-      *depth = sqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
+      *depth = tsg_sqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
       if (ccd_is_zero(pdir[0]) && ccd_is_zero(pdir[1]) && ccd_is_zero(pdir[2])) copy3(pdir, dir);
       ccd_normalize(pdir);
       copy3(dir_out, pdir);
@@ -521,7 +568,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
         cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
         sum = b[1] + b[2] + b[3];
       }
-      double inv = 1.0 / sum, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+      double inv = tsg_div(1.0, sum), p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
       // v0's second witness is obj2's centre
       for (int i = 0; i < 4; i++) {
         double v2[3];
@@ -558,21 +605,21 @@ TSG_FN double segseg_dist2(const double* p1, const double* a1, const double* p2,
   double r[3]; sub3(r, p1, p2);
   double A = dot3(a1, a1), E = dot3(a2, a2), Bq = dot3(a1, a2), C = dot3(a1, r), F = dot3(a2, r);
   double den = A * E - Bq * Bq, s = 0, t;
-  if (den > 1e-30) s = clampd((Bq * F - C * E) / den, -1.0, 1.0);
-  t = (Bq * s + F) / E;
-  if (t < -1.0) { t = -1.0; s = clampd((-Bq - C) / A, -1.0, 1.0); }
-  else if (t > 1.0) { t = 1.0; s = clampd((Bq - C) / A, -1.0, 1.0); }
+  if (den > 1e-30) s = clampd(tsg_div(Bq * F - C * E, den), -1.0, 1.0);
+  t = tsg_div(Bq * s + F, E);
+  if (t < -1.0) { t = -1.0; s = clampd(tsg_div(-Bq - C, A), -1.0, 1.0); }
+  else if (t > 1.0) { t = 1.0; s = clampd(tsg_div(Bq - C, A), -1.0, 1.0); }
   double d[3] = {r[0] + s * a1[0] - t * a2[0], r[1] + s * a1[1] - t * a2[1], r[2] + s * a1[2] - t * a2[2]};
   return dot3(d, d);
 }
 TSG_FN double ptseg_dist2(const double* c, const double* p, const double* a) {
   double r[3]; sub3(r, c, p);
-  double t = clampd(dot3(r, a) / dot3(a, a), -1.0, 1.0);
+  double t = clampd(tsg_div(dot3(r, a), dot3(a, a)), -1.0, 1.0);
   addscl3(r, a, -t);
   return dot3(r, r);
 }
 
-TSG_FN void plane_cylinder_points(const DevModel& m, const double* pos2, const double* axis_in, double radius, double half,
+TSG_FN_NOINLINE void plane_cylinder_points(const DevModel& m, const double* pos2, const double* axis_in, double radius, double half,
                                   const double* xaxis, int& cnt, double dist[4], double pts[4][3]) {
   const double* normal = m.fnormal;
   double axis[3], vec[3];
@@ -583,7 +630,7 @@ TSG_FN void plane_cylinder_points(const DevModel& m, const double* pos2, const d
   double dist0 = dot3(vec, normal);
   scl3(vec, axis, prjaxis); sub3(vec, vec, normal);
   double len_sqr = dot3(vec, vec);
-  if (len_sqr >= MINVAL * MINVAL) scl3(vec, vec, radius / sqrt(len_sqr));
+  if (len_sqr >= MINVAL * MINVAL) scl3(vec, vec, tsg_div(radius, tsg_sqrt(len_sqr)));
   else scl3(vec, xaxis, radius);
   double prjvec = dot3(vec, normal);
   scl3(axis, axis, half); prjaxis *= half;
@@ -601,7 +648,7 @@ TSG_FN void plane_cylinder_points(const DevModel& m, const double* pos2, const d
   double prjvec1 = -prjvec * 0.5;
   if (dist0 + prjaxis + prjvec1 <= 0) {
     double vec1[3];
-    cross3(vec1, vec, axis); normalize3(vec1); scl3(vec1, vec1, radius * sqrt(3.0) * 0.5);
+    cross3(vec1, vec, axis); normalize3(vec1); scl3(vec1, vec1, radius * tsg_sqrt(3.0) * 0.5);
     for (int s = 0; s < 2; s++) {
       dist[cnt] = dist0 + prjaxis + prjvec1;
       add3(pts[cnt], pos2, axis); addscl3(pts[cnt], vec1, s ? -1.0 : 1.0); addscl3(pts[cnt], vec, -0.5);
@@ -618,13 +665,14 @@ TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
     double dist[4], pts[4][3];
     if (g < NGEOM) {
       int b = g / 5;
-      const double* c = S.gpos + 3 * g;
-      double tmp[3]; sub3(tmp, c, m.fpos);
+      double c[3], tmp[3];
+      geom_center(S, m, g, c);
+      sub3(tmp, c, m.fpos);
       double cdist = dot3(tmp, m.fnormal);
       if (m.gtype[g] == GEOM_SPHERE) {
         double r = m.gsize[g][0];
         if (cdist <= r) { cnt = 1; dist[0] = cdist - r; copy3(pts[0], c); addscl3(pts[0], m.fnormal, -dist[0] / 2 - r); }
-      } else if (cdist <= sqrt(m.gsize[g][0] * m.gsize[g][0] + m.gsize[g][1] * m.gsize[g][1])) {
+      } else if (cdist <= tsg_sqrt(m.gsize[g][0] * m.gsize[g][0] + m.gsize[g][1] * m.gsize[g][1])) {
         const double* R = S.xmat + 9 * b;
         double axis[3] = {R[2], R[5], R[8]}, xaxis[3] = {R[0], R[3], R[6]};
         plane_cylinder_points(m, c, axis, m.gsize[g][0], m.gsize[g][1], xaxis, cnt, dist, pts);
@@ -635,7 +683,7 @@ TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
     if (need) {
       int b = g / 5;
       for (int k = 0; k < cnt; k++) {
-        if (slot + k < MAXC) set_contact(S.con[slot + k], -1, b, dist[k], pts[k], m.fnormal);
+        if (slot + k < MAXC) set_contact(con_at(S, slot + k), -1, b, dist[k], pts[k], m.fnormal);
         else S.overflow = 1;
       }
     }
@@ -645,7 +693,7 @@ TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
 // floor = height field (hfield frame axis-aligned at fpos): geom AABBs -> prism candidates -> MPR
 TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
   // prism k of row r: vertices n = k, k+1, k+2 of the strip (c = cmin + n/2, i = n%2 -> row r+1 / r)
-  double dx = (2.0 * m.hsize[0]) / (m.ncol - 1), dy = (2.0 * m.hsize[1]) / (m.nrow - 1);
+  double dx = tsg_div(2.0 * m.hsize[0], (double)(m.ncol - 1)), dy = tsg_div(2.0 * m.hsize[1], (double)(m.nrow - 1));
   for (int j = 0; j < 3; j++) {
     int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
     double x = dx * c - m.hsize[0], y = dy * rr - m.hsize[1];
@@ -657,9 +705,11 @@ TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
 TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) {
   LANE_FOR(g, NGEOM) {
     int b = g / 5;
-    double pos[3]; sub3(pos, S.gpos + 3 * g, m.fpos);
+    double pos[3], gc[3];
+    geom_center(S, m, g, gc);
+    sub3(pos, gc, m.fpos);
     double r = m.gsize[g][0], hl = m.gsize[g][1];
-    double rb = m.gtype[g] == GEOM_SPHERE ? r : sqrt(r * r + hl * hl);
+    double rb = m.gtype[g] == GEOM_SPHERE ? r : tsg_sqrt(r * r + hl * hl);
     bool ok = true;
     for (int i = 0; i < 2; i++) if (m.hsize[i] < pos[i] - rb || -m.hsize[i] > pos[i] + rb) ok = false;
     if (m.hsize[2] < pos[2] - rb || -m.hsize[3] > pos[2] + rb) ok = false;
@@ -669,156 +719,164 @@ TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) 
       const double* R = S.xmat + 9 * b;
       for (int i = 0; i < 3; i++) {
         double az = R[3 * i + 2];
-        ext[i] = r * sqrt(fmax(0.0, 1.0 - az * az)) + hl * fabs(az);
+        ext[i] = r * tsg_sqrt(fmax(0.0, 1.0 - az * az)) + hl * fabs(az);
       }
     }
     double xmin = pos[0] - ext[0], xmax = pos[0] + ext[0], ymin = pos[1] - ext[1], ymax = pos[1] + ext[1];
     double zmin = pos[2] - ext[2], zmax = pos[2] + ext[2];
     if (xmin > m.hsize[0] || xmax < -m.hsize[0] || ymin > m.hsize[1] || ymax < -m.hsize[1] || zmin > m.hsize[2] || zmax < -m.hsize[3]) ok = false;
-    int cmin = (int)floor((xmin + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
-    int cmax = (int)ceil((xmax + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
-    int rmin = (int)floor((ymin + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
-    int rmax = (int)ceil((ymax + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
+    int cmin = (int)floor(tsg_div(xmin + m.hsize[0], 2 * m.hsize[0]) * (m.ncol - 1));
+    int cmax = (int)ceil(tsg_div(xmax + m.hsize[0], 2 * m.hsize[0]) * (m.ncol - 1));
+    int rmin = (int)floor(tsg_div(ymin + m.hsize[1], 2 * m.hsize[1]) * (m.nrow - 1));
+    int rmax = (int)ceil(tsg_div(ymax + m.hsize[1], 2 * m.hsize[1]) * (m.nrow - 1));
     if (cmin < 0) cmin = 0;
     if (cmax > m.ncol - 1) cmax = m.ncol - 1;
     if (rmin < 0) rmin = 0;
     if (rmax > m.nrow - 1) rmax = m.nrow - 1;
     int per_row = 2 * (cmax - cmin + 1) - 2;
     if (!ok || per_row <= 0 || rmax <= rmin) { per_row = 0; rmax = rmin; }
-    S.hf_cell[g][0] = cmin; S.hf_cell[g][1] = per_row; S.hf_cell[g][2] = rmin; S.hf_cell[g][3] = rmax - rmin;
-    S.hf_zmin[g] = zmin;
+    S.u.col.hf_cell[g][0] = cmin; S.u.col.hf_cell[g][1] = per_row; S.u.col.hf_cell[g][2] = rmin; S.u.col.hf_cell[g][3] = rmax - rmin;
+    S.u.col.hf_zmin[g] = zmin;
   }
   WSYNC();
-  // candidates (geom, prism) in MuJoCo's order; chunks of MAXCAND go through MPR in parallel
+  // candidates (geom, prism) in MuJoCo's order, processed in blocks of MAXCAND items so the list cannot overflow
   constexpr int PMAX = 24;
-  int ncand = 0;
-  LANE_FOR_ALL(i, NGEOM * PMAX) {
-    int g = i / PMAX, p = i % PMAX, flag = 0;
-    if (g < NGEOM) {
-      int per_row = S.hf_cell[g][1], nrows = S.hf_cell[g][3];
-      if (per_row > 0 && p < per_row * nrows) {
-        int r = S.hf_cell[g][2] + p / per_row, k = p % per_row, cmin = S.hf_cell[g][0];
-        double zmin = S.hf_zmin[g];
-        flag = 0;
-        for (int j = 0; j < 3; j++) {
-          int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
-          if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
+  TSG_UNROLL1
+  for (int base = 0; base < NGEOM * PMAX; base += MAXCAND) {
+    int ncand = 0;
+    LANE_FOR_ALL(ii, MAXCAND) {
+      int i = base + ii, g = i / PMAX, p = i % PMAX, flag = 0;
+      if (ii < MAXCAND && g < NGEOM) {
+        int per_row = S.u.col.hf_cell[g][1], nrows = S.u.col.hf_cell[g][3];
+        if (per_row > 0 && p < per_row * nrows) {
+          int r = S.u.col.hf_cell[g][2] + p / per_row, k = p % per_row, cmin = S.u.col.hf_cell[g][0];
+          double zmin = S.u.col.hf_zmin[g];
+          for (int j = 0; j < 3; j++) {
+            int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
+            if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
+          }
         }
-      } else if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
+        if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
+      }
+      int slot = scan_slot(flag, ncand, lane);
+      if (flag) S.u.col.cand[slot] = i;
     }
-    int slot = scan_slot(flag, ncand, lane);
-    if (flag) { if (slot < MAXCAND) { S.cand[slot] = i; } else S.overflow = 1; }
-  }
-  if (ncand > MAXCAND) ncand = MAXCAND;
-  WSYNC();
-  LANE_FOR_ALL(n, ncand) {
-    bool hit = false;
-    double depth = 0, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
-    int b = 0;
-    if (n < ncand) {
-      int i = S.cand[n], g = i / PMAX, p = i % PMAX;
-      b = g / 5;
-      int per_row = S.hf_cell[g][1];
-      double prism[18];
-      hf_prism(m, S.hf_cell[g][2] + p / per_row, S.hf_cell[g][0], p % per_row, prism);
-      CObj o1, o2;
-      o1.type = 100; o1.prism = prism; o1.mat = nullptr;
-      o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b; o2.prism = nullptr;
-      sub3(o2.pos, S.gpos + 3 * g, m.fpos);
-      o2.size[0] = m.gsize[g][0]; o2.size[1] = m.gsize[g][1];
-      hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, pos);
-      if (hit && ccd_vec_is_origin(dir)) hit = false;
-      if (hit) {
-        add3(pos, pos, m.fpos);
-        if ((m.flags & 4u) && o2.type == GEOM_SPHERE) {
-          double nn[3]; sub3(nn, S.gpos + 3 * g, pos);
-          if (sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(dir, nn); }
+    WSYNC();
+    LANE_FOR_ALL(n, ncand) {
+      bool hit = false;
+      double depth = 0, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
+      int b = 0;
+      if (n < ncand) {
+        int i = S.u.col.cand[n], g = i / PMAX, p = i % PMAX;
+        b = g / 5;
+        int per_row = S.u.col.hf_cell[g][1];
+        double prism[18], gc[3];
+        hf_prism(m, S.u.col.hf_cell[g][2] + p / per_row, S.u.col.hf_cell[g][0], p % per_row, prism);
+        CObj o1, o2;
+        o1.type = 100; o1.prism = prism; o1.mat = nullptr;
+        o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b; o2.prism = nullptr;
+        geom_center(S, m, g, gc);
+        sub3(o2.pos, gc, m.fpos);
+        o2.size[0] = m.gsize[g][0]; o2.size[1] = m.gsize[g][1];
+        hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, pos);
+        if (hit && ccd_vec_is_origin(dir)) hit = false;
+        if (hit) {
+          add3(pos, pos, m.fpos);
+          if ((m.flags & 4u) && o2.type == GEOM_SPHERE) {
+            double nn[3]; sub3(nn, gc, pos);
+            if (tsg_sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(dir, nn); }
+          }
         }
       }
+      int slot = scan_slot(hit ? 1 : 0, nslot, lane);
+      if (hit) { if (slot < MAXC) set_contact(con_at(S, slot), -1, b, -depth, pos, dir); else S.overflow = 1; }
     }
-    int slot = scan_slot(hit ? 1 : 0, nslot, lane);
-    if (hit) { if (slot < MAXC) set_contact(S.con[slot], -1, b, -depth, pos, dir); else S.overflow = 1; }
+    if (lane == 0) S.nmpr_total += ncand;
+    if (nslot > MAXC) nslot = MAXC;
+    WSYNC();
   }
-  if (lane == 0) S.nmpr_total += ncand;
-  if (nslot > MAXC) nslot = MAXC;
-  WSYNC();
 }
 
 // bar-bar: 75 geom pairs, analytic capsule pre-filter (conservative), then sphere-sphere / MPR
 TSG_FN void collide_bars(Scratch& S, const DevModel& m, int lane, int& nslot) {
-  int ncand = 0;
-  LANE_FOR_ALL(i, 75) {
-    int flag = 0;
-    if (i < 75) {
-      int pr = i / 25, b1 = pr == 2 ? 1 : 0, b2 = pr == 0 ? 1 : 2;
-      int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
-      int t1 = m.gtype[g1], t2 = m.gtype[g2];
-      const double *c1 = S.gpos + 3 * g1, *c2 = S.gpos + 3 * g2;
-      double rs = m.gsize[g1][0] + m.gsize[g2][0] + 1e-6;
-      const double *R1 = S.xmat + 9 * b1, *R2 = S.xmat + 9 * b2;
-      double a1[3] = {R1[2] * m.gsize[g1][1], R1[5] * m.gsize[g1][1], R1[8] * m.gsize[g1][1]};
-      double a2[3] = {R2[2] * m.gsize[g2][1], R2[5] * m.gsize[g2][1], R2[8] * m.gsize[g2][1]};
-      double d2;
-      if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) { double d[3]; sub3(d, c1, c2); d2 = dot3(d, d); }
-      else if (t1 == GEOM_SPHERE) d2 = ptseg_dist2(c1, c2, a2);
-      else if (t2 == GEOM_SPHERE) d2 = ptseg_dist2(c2, c1, a1);
-      else d2 = segseg_dist2(c1, a1, c2, a2);
-      flag = d2 <= rs * rs;
+  TSG_UNROLL1
+  for (int base = 0; base < 75; base += MAXCAND) {
+    int ncand = 0;
+    LANE_FOR_ALL(ii, MAXCAND) {
+      int flag = 0, i = base + ii;
+      if (ii < MAXCAND && i < 75) {
+        int pr = i / 25, b1 = pr == 2 ? 1 : 0, b2 = pr == 0 ? 1 : 2;
+        int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
+        int t1 = m.gtype[g1], t2 = m.gtype[g2];
+        double c1[3], c2[3];
+        geom_center(S, m, g1, c1); geom_center(S, m, g2, c2);
+        double rs = m.gsize[g1][0] + m.gsize[g2][0] + 1e-6;
+        const double *R1 = S.xmat + 9 * b1, *R2 = S.xmat + 9 * b2;
+        double a1[3] = {R1[2] * m.gsize[g1][1], R1[5] * m.gsize[g1][1], R1[8] * m.gsize[g1][1]};
+        double a2[3] = {R2[2] * m.gsize[g2][1], R2[5] * m.gsize[g2][1], R2[8] * m.gsize[g2][1]};
+        double d2;
+        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) { double d[3]; sub3(d, c1, c2); d2 = dot3(d, d); }
+        else if (t1 == GEOM_SPHERE) d2 = ptseg_dist2(c1, c2, a2);
+        else if (t2 == GEOM_SPHERE) d2 = ptseg_dist2(c2, c1, a1);
+        else d2 = segseg_dist2(c1, a1, c2, a2);
+        flag = d2 <= rs * rs;
+      }
+      int slot = scan_slot(flag, ncand, lane);
+      if (flag) S.u.col.cand[slot] = i;
     }
-    int slot = scan_slot(flag, ncand, lane);
-    if (flag) { if (slot < MAXCAND) S.cand[slot] = i; else S.overflow = 1; }
-  }
-  if (ncand > MAXCAND) ncand = MAXCAND;
-  WSYNC();
-  LANE_FOR_ALL(n, ncand) {
-    bool hit = false;
-    double dist = 1, pos[3] = {0, 0, 0}, nrm[3] = {1, 0, 0};
-    int b1 = 0, b2 = 1;
-    if (n < ncand) {
-      int i = S.cand[n];
-      int pr = i / 25;
-      b1 = pr == 2 ? 1 : 0; b2 = pr == 0 ? 1 : 2;
-      int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
-      if (m.gtype[g1] > m.gtype[g2]) { int t = g1; g1 = g2; g2 = t; t = b1; b1 = b2; b2 = t; }  // lower type first
-      const double *c1 = S.gpos + 3 * g1, *c2 = S.gpos + 3 * g2;
-      if (m.gtype[g2] == GEOM_SPHERE) {
-        sub3(nrm, c2, c1);
-        double len = normalize3(nrm), r1 = m.gsize[g1][0];
-        dist = len - r1 - m.gsize[g2][0];
-        hit = dist <= 0;
-        copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
-      } else {
-        CObj o1, o2;
-        o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; o1.prism = nullptr; copy3(o1.pos, c1);
-        o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
-        o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; o2.prism = nullptr; copy3(o2.pos, c2);
-        o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
-        double depth;
-        hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
-        if (hit && ccd_vec_is_origin(nrm)) hit = false;
-        dist = -depth;
-        if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
-          double nn[3]; sub3(nn, pos, c1);
-          if (sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(nrm, nn); }
+    WSYNC();
+    LANE_FOR_ALL(n, ncand) {
+      bool hit = false;
+      double dist = 1, pos[3] = {0, 0, 0}, nrm[3] = {1, 0, 0};
+      int b1 = 0, b2 = 1;
+      if (n < ncand) {
+        int i = S.u.col.cand[n];
+        int pr = i / 25;
+        b1 = pr == 2 ? 1 : 0; b2 = pr == 0 ? 1 : 2;
+        int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
+        if (m.gtype[g1] > m.gtype[g2]) { int t = g1; g1 = g2; g2 = t; t = b1; b1 = b2; b2 = t; }  // lower type first
+        double c1[3], c2[3];
+        geom_center(S, m, g1, c1); geom_center(S, m, g2, c2);
+        if (m.gtype[g2] == GEOM_SPHERE) {
+          sub3(nrm, c2, c1);
+          double len = normalize3(nrm), r1 = m.gsize[g1][0];
+          dist = len - r1 - m.gsize[g2][0];
+          hit = dist <= 0;
+          copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
+        } else {
+          CObj o1, o2;
+          o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; o1.prism = nullptr; copy3(o1.pos, c1);
+          o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
+          o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; o2.prism = nullptr; copy3(o2.pos, c2);
+          o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
+          double depth;
+          hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
+          if (hit && ccd_vec_is_origin(nrm)) hit = false;
+          dist = -depth;
+          if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
+            double nn[3]; sub3(nn, pos, c1);
+            if (tsg_sqrt(dot3(nn, nn)) > MINVAL) { normalize3(nn); copy3(nrm, nn); }
+          }
         }
       }
+      int slot = scan_slot(hit ? 1 : 0, nslot, lane);
+      if (hit) { if (slot < MAXC) set_contact(con_at(S, slot), b1, b2, dist, pos, nrm); else S.overflow = 1; }
     }
-    int slot = scan_slot(hit ? 1 : 0, nslot, lane);
-    if (hit) { if (slot < MAXC) set_contact(S.con[slot], b1, b2, dist, pos, nrm); else S.overflow = 1; }
+    if (lane == 0) S.nmpr_total += ncand;
+    if (nslot > MAXC) nslot = MAXC;
+    WSYNC();
   }
-  if (lane == 0) S.nmpr_total += ncand;
-  if (nslot > MAXC) nslot = MAXC;
-  WSYNC();
 }
 
 TSG_FN double impedance(const DevModel& m, double pos) {
   double d0 = clampd(m.solimp[0], MINIMP, MAXIMP), dw = clampd(m.solimp[1], MINIMP, MAXIMP);
   double width = fmax(MINVAL, m.solimp[2]), mid = clampd(m.solimp[3], MINIMP, MAXIMP), power = fmax(1.0, m.solimp[4]);
   if (d0 == dw || width <= MINVAL) return 0.5 * (d0 + dw);
-  double x = fabs(pos) / width, y;
+  double x = tsg_div(fabs(pos), width), y;
   if (x >= 1) return dw;
   if (x == 0) return d0;
   if (power == 1) y = x;
+  else if (power == 2) y = (x <= mid) ? tsg_div(1.0, mid) * (x * x) : 1 - tsg_div(1.0, 1 - mid) * ((1 - x) * (1 - x));
   else if (x <= mid) y = (1 / pow(mid, power - 1)) * pow(x, power);
   else y = 1 - (1 / pow(1 - mid, power - 1)) * pow(1 - x, power);
   return d0 + y * (dw - d0);
@@ -833,7 +891,7 @@ TSG_FN void stage_constraint(Scratch& S, const DevModel& m, int lane) {
   // compact the active slots
   int nact = 0;
   LANE_FOR_ALL(s, MAXC) {
-    int flag = (s < nslot) && S.con[s].active;
+    int flag = (s < nslot) && con_at(S, s < nslot ? s : 0).active;
     int k = scan_slot(flag, nact, lane);
     if (flag) S.order[k] = s;
   }
@@ -841,34 +899,32 @@ TSG_FN void stage_constraint(Scratch& S, const DevModel& m, int lane) {
   WSYNC();
   // Jacobian blocks: item = (contact, side, axis)
   LANE_FOR(i, nact * 6) {
-    Con& c = S.con[S.order[i / 6]];
+    Con& c = con_at(S, S.order[i / 6]);
     int side = (i % 6) / 3, ax = i % 3, b = side ? c.b2 : c.b1;
-    double* Jt = c.J[side][ax];
-    double* Jr = c.J[side][3 + ax];
-    if (b < 0) { for (int k = 0; k < 6; k++) { Jt[k] = 0; Jr[k] = 0; } }
+    double* Jt = c.Jt[side][ax];
+    double* Jr = c.Jr[side][ax];
+    if (b < 0) { for (int k = 0; k < 3; k++) { Jt[k] = 0; Jr[k] = 0; } }
     else {
       double s = side ? 1.0 : -1.0, rr[3], t[3], w[3];
       const double* a = c.frame + 3 * ax;
       sub3(rr, c.pos, S.qpos + 7 * b);
       cross3(t, rr, a);
       mulMTV(w, S.xmat + 9 * b, t);
-      Jt[0] = s * a[0]; Jt[1] = s * a[1]; Jt[2] = s * a[2]; Jt[3] = s * w[0]; Jt[4] = s * w[1]; Jt[5] = s * w[2];
+      Jt[0] = s * w[0]; Jt[1] = s * w[1]; Jt[2] = s * w[2];
       mulMTV(w, S.xmat + 9 * b, a);
-      Jr[0] = Jr[1] = Jr[2] = 0; Jr[3] = s * w[0]; Jr[4] = s * w[1]; Jr[5] = s * w[2];
+      Jr[0] = s * w[0]; Jr[1] = s * w[1]; Jr[2] = s * w[2];
     }
   }
   WSYNC();
   // rows: velocity, impedance, reference acceleration; item = (contact, row)
   LANE_FOR(i, nact * 6) {
-    Con& c = S.con[S.order[i / 6]];
+    Con& c = con_at(S, S.order[i / 6]);
     int r = i % 6;
-    double vel = 0;
-    if (c.b1 >= 0) for (int k = 0; k < 6; k++) vel += c.J[0][r][k] * S.qvel[6 * c.b1 + k];
-    for (int k = 0; k < 6; k++) vel += c.J[1][r][k] * S.qvel[6 * c.b2 + k];
+    double vel = Jrow_dot_all(c, r, S.qvel);
     double imp = impedance(m, c.dist);
     if (r == 0) {
       double tran = (c.b1 >= 0 ? m.invw_tran[c.b1] : 0.0) + m.invw_tran[c.b2];
-      c.D0 = 1 / fmax(MINVAL, (1 - imp) / imp * tran);
+      c.D0 = tsg_div(1.0, fmax(MINVAL, tsg_div(1 - imp, imp) * tran));
     }
     c.aref[r] = -m.B * vel - (r ? 0.0 : m.K * imp * c.dist);
   }
@@ -876,14 +932,16 @@ TSG_FN void stage_constraint(Scratch& S, const DevModel& m, int lane) {
 }
 
 // ------------------------------------------------------------------ Newton solver
-TSG_FN void compute_jar(Scratch& S, const double* a, int lane) {
+// (every routine that is called from more than one place exists once, out of line: see tsg_sqrt above)
+enum { VEC_SMOOTH = 0, VEC_WARM = 1, VEC_QACC = 2 };
+// jar = J a - aref for a = qacc_smooth / warm start / qacc
+TSG_FN_NOINLINE void compute_jar(int which, CTX_PARAMS) {
+  CTX_BIND
+  const double* a = which == VEC_SMOOTH ? S.asmooth : (which == VEC_WARM ? S.warm : S.qacc);
   LANE_FOR(i, S.nact * 6) {
-    Con& c = S.con[S.order[i / 6]];
+    Con& k = con_at(S, S.order[i / 6]);
     int r = i % 6;
-    double v = 0;
-    if (c.b1 >= 0) for (int k = 0; k < 6; k++) v += c.J[0][r][k] * a[6 * c.b1 + k];
-    for (int k = 0; k < 6; k++) v += c.J[1][r][k] * a[6 * c.b2 + k];
-    c.jar[r] = v - c.aref[r];
+    k.jar[r] = Jrow_dot_all(k, r, a) - k.aref[r];
   }
   WSYNC();
 }
@@ -893,9 +951,9 @@ TSG_FN double con_update(Con& c, const DevModel& m, bool full) {
   U[0] = c.jar[0] * mu;
   for (int j = 1; j < 6; j++) { U[j] = c.jar[j] * m.fr[j - 1]; T += U[j] * U[j]; }
   double N = U[0];
-  T = sqrt(T);
+  T = tsg_sqrt(T);
   if (N >= mu * T || (T <= 0 && N >= 0)) {
-    if (full) { for (int j = 0; j < 6; j++) { c.force[j] = 0; c.w[j] = 0; } c.zone = ZONE_TOP; c.ca = c.cb = 0; }
+    if (full) { for (int j = 0; j < 6; j++) c.force[j] = 0; c.zone = ZONE_TOP; c.wcoef = c.ca = c.cb = 0; }
     return 0;
   }
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
@@ -903,277 +961,324 @@ TSG_FN double con_update(Con& c, const DevModel& m, bool full) {
     for (int j = 0; j < 6; j++) {
       double D = c.D0 * m.dscale[j];
       s += 0.5 * D * c.jar[j] * c.jar[j];
-      if (full) { c.force[j] = -D * c.jar[j]; c.w[j] = D; }
+      if (full) c.force[j] = -D * c.jar[j];
     }
-    if (full) { c.zone = ZONE_BOTTOM; c.ca = c.cb = 0; }
+    if (full) { c.zone = ZONE_BOTTOM; c.wcoef = c.D0; c.ca = c.cb = 0; }
     return s;
   }
-  double Dm = c.D0 / (mu * mu * (1 + mu * mu)), NT = N - mu * T;
+  double Dm = c.D0 * m.inv_mu2, NT = N - mu * T;
   if (full) {
+    double invT = tsg_div(1.0, T);
     c.force[0] = -Dm * NT * mu;
-    double kap = mu * mu - mu * N / T;
-    c.w[0] = 0; c.su[0] = 0;
+    double kap = mu * mu - mu * N * invT;
+    c.su[0] = 0;
     for (int j = 1; j < 6; j++) {
-      c.force[j] = -c.force[0] / T * U[j] * m.fr[j - 1];
-      c.w[j] = Dm * kap * m.fr[j - 1] * m.fr[j - 1];
-      c.su[j] = m.fr[j - 1] * U[j] / T;
+      c.force[j] = -c.force[0] * invT * U[j] * m.fr[j - 1];
+      c.su[j] = m.fr[j - 1] * U[j] * invT;
     }
-    c.ca = Dm; c.cb = Dm * kap; c.zone = ZONE_MIDDLE;
+    c.ca = Dm; c.cb = Dm * kap; c.wcoef = c.cb; c.zone = ZONE_MIDDLE;
   }
   return 0.5 * Dm * NT * NT;
 }
-// cost of candidate acceleration a: constraint part via S.red, Gauss part added by the caller
-TSG_FN double constraint_cost(Scratch& S, const DevModel& m, int lane, bool full) {
-  LANE_FOR(n, S.nact) S.red[n] = con_update(S.con[S.order[n]], m, full);
+// total cost at `which` (constraint part summed over contacts through the shared accumulator + Gauss part);
+// full: also forces / zones / Hessian weights.  The Gauss part alone is left in S.gauss.
+TSG_FN_NOINLINE double total_cost(int which, int full, CTX_PARAMS) {
+  CTX_BIND
+  LANE_FOR(n, S.nact) S.u.ls.acc[n][0] = con_update(con_at(S, S.order[n]), m, full != 0);
   WSYNC();
   double s = 0;
-  for (int n = 0; n < S.nact; n++) s += S.red[n];
-  WSYNC();
-  return s;
-}
-TSG_FN double gauss_cost(const Scratch& S, const DevModel& m, const double* a) {
+  TSG_UNROLL1
+  for (int n = 0; n < S.nact; n++) s += S.u.ls.acc[n][0];
   double g = 0;
-  for (int k = 0; k < NV; k++) { double d = a[k] - S.asmooth[k]; g += 0.5 * m.M[k] * d * d; }
-  return g;
-}
-// gradient, Hessian, Cholesky, search = -H^-1 grad.  Needs con_update(full) done.
-TSG_FN void newton_direction(Scratch& S, const DevModel& m, int lane) {
-  int nact = S.nact;
-  // cone vectors b = sum_j su_j J_j  (item = contact, side, dof)
-  LANE_FOR(i, nact * 12) {
-    Con& c = S.con[S.order[i / 12]];
-    if (c.zone == ZONE_MIDDLE) {
-      int side = (i % 12) / 6, k = i % 6;
-      double v = 0;
-      for (int j = 1; j < 6; j++) v += c.su[j] * c.J[side][j][k];
-      c.bvec[side][k] = v;
-    }
-  }
-  // gradient + qfrc_constraint (item = dof)
-  LANE_FOR(i, NV) {
-    int b = i / 6, k = i % 6;
-    double f = 0;
-    for (int n = 0; n < nact; n++) {
-      const Con& c = S.con[S.order[n]];
-      int side = c.b2 == b ? 1 : (c.b1 == b ? 0 : -1);
-      if (side < 0) continue;
-      for (int r = 0; r < 6; r++) f += c.J[side][r][k] * c.force[r];
-    }
-    S.fcon[i] = f;
-    S.grad[i] = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
+  if (which != VEC_SMOOTH) {
+    const double* a = which == VEC_WARM ? S.warm : S.qacc;
+    TSG_UNROLL1
+    for (int k = 0; k < NV; k++) { double d = a[k] - S.asmooth[k]; g += 0.5 * m.M[k] * d * d; }
   }
   WSYNC();
-  // Hessian lower triangle (item = entry)
-  LANE_FOR(e, NV * (NV + 1) / 2) {
-    int i = 0; while ((i + 1) * (i + 2) / 2 <= e) i++;
-    int j = e - i * (i + 1) / 2;
-    int bi = i / 6, ki = i % 6, bj = j / 6, kj = j % 6;
-    double v = (i == j) ? m.M[i] : 0.0;
-    for (int n = 0; n < nact; n++) {
-      const Con& c = S.con[S.order[n]];
-      if (c.zone == ZONE_TOP) continue;
-      int si = c.b2 == bi ? 1 : (c.b1 == bi ? 0 : -1);
-      int sj = c.b2 == bj ? 1 : (c.b1 == bj ? 0 : -1);
-      if (si < 0 || sj < 0) continue;
-      for (int r = 0; r < 6; r++) v += c.w[r] * c.J[si][r][ki] * c.J[sj][r][kj];
-      if (c.zone == ZONE_MIDDLE) {
-        double bi_ = c.bvec[si][ki], bj_ = c.bvec[sj][kj];
-        double ai = m.mu * (c.J[si][0][ki] - bi_), aj = m.mu * (c.J[sj][0][kj] - bj_);
-        v += c.ca * ai * aj - c.cb * bi_ * bj_;
-      }
-    }
-    S.H[i * HS + j] = v;
-  }
+  S.gauss = g;
+  return s + g;
+}
+
+// H = L D L^T of the packed Hessian in shared memory (lane i owns row i; no square roots; structurally zero
+// columns -- bars not coupled by a contact -- are skipped), then forward / diagonal / backward substitution
+TSG_FN void factor_solve(Scratch& S, int lane) {
+  double* H = S.u.hes.H;
   LANE_FOR(i, NV) S.rhs[i] = S.grad[i];
   WSYNC();
-  // Cholesky (row i owned by lane i), then forward / backward substitution
-  for (int k = 0; k < NV; k++) {
-    double piv = sqrt(fmax(S.H[k * HS + k], MINVAL)), inv = 1.0 / piv;
-    LANE_FOR(i, NV) {
-      if (i == k) S.dinv[k] = inv;
-      if (i > k) S.H[i * HS + k] *= inv;
-    }
-    WSYNC();
+  TSG_UNROLL1
+  for (int k = 0; k < NV - 1; k++) {
+    int kk = k * (k + 1) / 2;
+    double dk = fmax(H[kk + k], MINVAL), inv = tsg_rcp(dk);
+    // column k still holds the raw entries t_ik = L_ik d_k during the update (read by every lane)
     LANE_FOR(i, NV) if (i > k) {
-      double lik = S.H[i * HS + k];
-      for (int j = k + 1; j <= i; j++) S.H[i * HS + j] -= lik * S.H[j * HS + k];
+      double* Hi = H + i * (i + 1) / 2;
+      double t = Hi[k];
+      if (t != 0.0) {
+        double lik = t * inv;
+        TSG_UNROLL1
+        for (int j = k + 1; j < i; j++) Hi[j] -= lik * H[j * (j + 1) / 2 + k];
+        Hi[i] -= lik * t;
+      }
     }
     WSYNC();
-  }
-  for (int k = 0; k < NV; k++) {
-    double yk = S.rhs[k] * S.dinv[k];
-    WSYNC();
-    LANE_FOR(i, NV) { if (i == k) S.rhs[k] = yk; else if (i > k) S.rhs[i] -= S.H[i * HS + k] * yk; }
+    LANE_FOR(i, NV) { if (i > k) H[i * (i + 1) / 2 + k] *= inv; else if (i == k) S.dinv[k] = inv; }
     WSYNC();
   }
-  for (int k = NV - 1; k >= 0; k--) {
-    double xk = S.rhs[k] * S.dinv[k];
+  if (lane == 0) S.dinv[NV - 1] = tsg_rcp(fmax(H[NTRI - 1], MINVAL));
+  WSYNC();
+  TSG_UNROLL1
+  for (int k = 0; k < NV - 1; k++) {   // L y = g (unit diagonal)
+    double yk = S.rhs[k];
     WSYNC();
-    LANE_FOR(i, NV) { if (i == k) S.rhs[k] = xk; else if (i < k) S.rhs[i] -= S.H[k * HS + i] * xk; }
+    LANE_FOR(i, NV) if (i > k) { double l = H[i * (i + 1) / 2 + k]; if (l != 0.0) S.rhs[i] -= l * yk; }
+    WSYNC();
+  }
+  LANE_FOR(i, NV) S.rhs[i] *= S.dinv[i];
+  WSYNC();
+  TSG_UNROLL1
+  for (int k = NV - 1; k > 0; k--) {   // L^T x = z
+    double xk = S.rhs[k];
+    WSYNC();
+    LANE_FOR(i, NV) if (i < k) { double l = H[k * (k + 1) / 2 + i]; if (l != 0.0) S.rhs[i] -= l * xk; }
     WSYNC();
   }
   LANE_FOR(i, NV) S.search[i] = -S.rhs[i];
   WSYNC();
 }
 
-struct LsPnt { double alpha, cost, d0, d1; };
-struct LsCtx { double qG0, qG1, qG2; int parity; int evals; };
+// column k (0..5) of the side's 6x6 Jacobian block
+TSG_FN void Jcol(const Con& c, int side, int k, double* col) {
+  if (k < 3) {
+    double s = side ? 1.0 : -1.0;
+    col[0] = s * c.frame[k]; col[1] = s * c.frame[3 + k]; col[2] = s * c.frame[6 + k];
+    col[3] = col[4] = col[5] = 0;
+  } else {
+    col[0] = c.Jt[side][0][k - 3]; col[1] = c.Jt[side][1][k - 3]; col[2] = c.Jt[side][2][k - 3];
+    col[3] = c.Jr[side][0][k - 3]; col[4] = c.Jr[side][1][k - 3]; col[5] = c.Jr[side][2][k - 3];
+  }
+}
 
-TSG_FN void ls_eval(Scratch& S, const DevModel& m, int lane, LsCtx& L, LsPnt& p) {
-  double a = p.alpha, mu = m.mu;
-  int par = L.parity; L.parity ^= 1;
+// gradient, Hessian, Cholesky, search = -H^-1 grad.  Needs total_cost(.., full) done.
+TSG_FN_NOINLINE void newton_direction(CTX_PARAMS) {
+  CTX_BIND
+  int nact = S.nact;
+  // cone vectors b = sum_j su_j J_j  (item = contact, side, dof)
+  LANE_FOR(i, nact * 12) {
+    Con& k = con_at(S, S.order[i / 12]);
+    if (k.zone == ZONE_MIDDLE) {
+      int side = (i % 12) / 6, d = i % 6;
+      double col[6], v = 0;
+      Jcol(k, side, d, col);
+      for (int j = 1; j < 6; j++) v += k.su[j] * col[j];
+      k.bvec[side][d] = v;
+    }
+  }
+  // gradient + qfrc_constraint (item = dof)
+  LANE_FOR(i, NV) {
+    int b = i / 6, d = i % 6;
+    double f = 0;
+    TSG_UNROLL1
+    for (int n = 0; n < nact; n++) {
+      const Con& k = con_at(S, S.order[n]);
+      int side = k.b2 == b ? 1 : (k.b1 == b ? 0 : -1);
+      if (side < 0) continue;
+      double col[6];
+      Jcol(k, side, d, col);
+      for (int r = 0; r < 6; r++) f += col[r] * k.force[r];
+    }
+    S.fcon[i] = f;
+    S.grad[i] = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
+  }
+  WSYNC();
+  // Hessian, packed lower triangle (item = entry)
+  LANE_FOR(e, NTRI) {
+    int i = m.tri_i[e], j = m.tri_j[e];
+    int bi = i / 6, ki = i % 6, bj = j / 6, kj = j % 6;
+    double v = (i == j) ? m.M[i] : 0.0;
+    TSG_UNROLL1
+    for (int n = 0; n < nact; n++) {
+      const Con& k = con_at(S, S.order[n]);
+      if (k.zone == ZONE_TOP) continue;
+      int si = k.b2 == bi ? 1 : (k.b1 == bi ? 0 : -1);
+      int sj = k.b2 == bj ? 1 : (k.b1 == bj ? 0 : -1);
+      if (si < 0 || sj < 0) continue;
+      const double* wt = m.wtab[k.zone == ZONE_MIDDLE ? 1 : 0];
+      double ci[6], cj[6], acc = 0;
+      Jcol(k, si, ki, ci); Jcol(k, sj, kj, cj);
+      for (int r = 0; r < 6; r++) acc += wt[r] * ci[r] * cj[r];
+      v += k.wcoef * acc;
+      if (k.zone == ZONE_MIDDLE) {
+        double bi_ = k.bvec[si][ki], bj_ = k.bvec[sj][kj];
+        double ai = m.mu * (ci[0] - bi_), aj = m.mu * (cj[0] - bj_);
+        v += k.ca * ai * aj - k.cb * bi_ * bj_;
+      }
+    }
+    S.u.hes.H[e] = v;
+  }
+  WSYNC();
+  factor_solve(S, lane);
+}
+
+struct LsPnt { double alpha, cost, d0, d1; };
+
+// cost and its first two derivatives along the search direction at step alpha -> S.lsr[0..2]
+TSG_FN_NOINLINE void ls_eval(double a, CTX_PARAMS) {
+  CTX_BIND
+  double mu = m.mu;
   LANE_FOR(n, S.nact) {
-    const Con& c = S.con[S.order[n]];
+    const Con& k = con_at(S, S.order[n]);
     double cost = 0, d0 = 0, d1 = 0;
-    double N = c.U0 + a * c.V0, Tsqr = c.UU + a * (2 * c.UV + a * c.VV);
+    double N = k.U0 + a * k.V0, Tsqr = k.UU + a * (2 * k.UV + a * k.VV);
     bool bottom = false;
     if (Tsqr <= 0) { if (N < 0) bottom = true; }
     else {
-      double T = sqrt(Tsqr);
+      double T = tsg_sqrt(Tsqr);
       if (N >= mu * T) {}
       else if (mu * N + T <= 0) bottom = true;
       else {
-        double N1 = c.V0, T1 = (c.UV + a * c.VV) / T;
-        double T2 = c.VV / T - (c.UV + a * c.VV) * T1 / (T * T);
-        double NT = N - mu * T, Dm = c.D0 / (mu * mu * (1 + mu * mu));
+        double invT = tsg_div(1.0, T);
+        double N1 = k.V0, T1 = (k.UV + a * k.VV) * invT;
+        double T2 = k.VV * invT - (k.UV + a * k.VV) * T1 * (invT * invT);
+        double NT = N - mu * T, Dm = k.D0 * m.inv_mu2;
         cost = 0.5 * Dm * NT * NT;
         d0 = Dm * NT * (N1 - mu * T1);
         d1 = Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NT * (-mu * T2));
       }
     }
-    if (bottom) { cost = a * a * c.q2 + a * c.q1 + c.q0; d0 = 2 * a * c.q2 + c.q1; d1 = 2 * c.q2; }
-    S.lsacc[par][n][0] = cost; S.lsacc[par][n][1] = d0; S.lsacc[par][n][2] = d1;
+    if (bottom) { cost = a * a * k.q2 + a * k.q1 + k.q0; d0 = 2 * a * k.q2 + k.q1; d1 = 2 * k.q2; }
+    S.u.ls.acc[n][0] = cost; S.u.ls.acc[n][1] = d0; S.u.ls.acc[n][2] = d1;
   }
   WSYNC();
-  double cost = a * a * L.qG2 + a * L.qG1 + L.qG0, d0 = 2 * a * L.qG2 + L.qG1, d1 = 2 * L.qG2;
-  for (int n = 0; n < S.nact; n++) { cost += S.lsacc[par][n][0]; d0 += S.lsacc[par][n][1]; d1 += S.lsacc[par][n][2]; }
+  double cost = a * a * S.qG[2] + a * S.qG[1] + S.qG[0], d0 = 2 * a * S.qG[2] + S.qG[1], d1 = 2 * S.qG[2];
+  TSG_UNROLL1
+  for (int n = 0; n < S.nact; n++) { cost += S.u.ls.acc[n][0]; d0 += S.u.ls.acc[n][1]; d1 += S.u.ls.acc[n][2]; }
+  WSYNC();
   if (d1 <= 0) d1 = MINVAL;
-  p.cost = cost; p.d0 = d0; p.d1 = d1;
-  L.evals++;
+  S.lsr[0] = cost; S.lsr[1] = d0; S.lsr[2] = d1;  // every lane writes the same values
+  if (lane == 0) S.ls_evals++;
+  WSYNC();
 }
-TSG_FN int ls_update_bracket(Scratch& S, const DevModel& m, int lane, LsCtx& L, LsPnt& p, const LsPnt* cand, LsPnt& pnext) {
+TSG_FN void ls_point(LsPnt& p, double alpha, EnvScratch& S, const DevModel& m, const EnvCfg& c, int lane) {
+  p.alpha = alpha;
+  ls_eval(alpha, CTX_ARGS);
+  p.cost = S.lsr[0]; p.d0 = S.lsr[1]; p.d1 = S.lsr[2];
+}
+TSG_FN int ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, EnvScratch& S, const DevModel& m, const EnvCfg& c, int lane) {
   int flag = 0;
   for (int i = 0; i < 3; i++) {
     if (p.d0 < 0 && cand[i].d0 < 0 && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
     else if (p.d0 > 0 && cand[i].d0 > 0 && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
   }
-  if (flag) { pnext.alpha = p.alpha - p.d0 / p.d1; ls_eval(S, m, lane, L, pnext); }
+  if (flag) ls_point(pnext, p.alpha - tsg_div(p.d0, p.d1), S, m, c, lane);
   return flag;
 }
-// exact line search along S.search from S.qacc (jar current); returns alpha. gauss = current Gauss cost
-TSG_FN double line_search(Scratch& S, const DevModel& m, int lane, double gauss, int& evals_out) {
-  double snorm = 0;
-  for (int k = 0; k < NV; k++) snorm += S.search[k] * S.search[k];
-  snorm = sqrt(snorm);
-  evals_out = 0;
-  if (snorm < MINVAL) return 0;
-  double scale = 1 / (m.meaninertia * NV);
-  double gtol = m.tol * m.ls_tol * snorm / scale;
-  LsCtx L; L.parity = 0; L.evals = 0;
-  L.qG0 = gauss; L.qG1 = 0; L.qG2 = 0;
+// exact line search along S.search from S.qacc (jar current, S.gauss = current Gauss cost); returns alpha
+TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
+  CTX_BIND
+  double snorm = 0, qG1 = 0, qG2 = 0;
+  TSG_UNROLL1
   for (int k = 0; k < NV; k++) {
-    L.qG1 += S.search[k] * (m.M[k] * S.qacc[k]) - S.fsm[k] * S.search[k];
-    L.qG2 += 0.5 * S.search[k] * (m.M[k] * S.search[k]);
+    double sk = S.search[k];
+    snorm += sk * sk;
+    qG1 += sk * (m.M[k] * S.qacc[k]) - S.fsm[k] * sk;
+    qG2 += 0.5 * sk * (m.M[k] * sk);
   }
-  // jv = J search ; per-contact quadratic / cone coefficients
+  snorm = tsg_sqrt(snorm);
+  if (snorm < MINVAL) return 0;
+  double gtol = m.tol * m.ls_tol * snorm * (m.meaninertia * NV);
+  WSYNC();
+  S.qG[0] = S.gauss; S.qG[1] = qG1; S.qG[2] = qG2; S.ls_evals = 0;
+  // jv = J search (stored over aref, which is dead by now)
   LANE_FOR(i, S.nact * 6) {
-    Con& c = S.con[S.order[i / 6]];
+    Con& k = con_at(S, S.order[i / 6]);
     int r = i % 6;
-    double v = 0;
-    if (c.b1 >= 0) for (int k = 0; k < 6; k++) v += c.J[0][r][k] * S.search[6 * c.b1 + k];
-    for (int k = 0; k < 6; k++) v += c.J[1][r][k] * S.search[6 * c.b2 + k];
-    c.jv[r] = v;
+    k.aref[r] = Jrow_dot_all(k, r, S.search);
   }
   WSYNC();
   LANE_FOR(n, S.nact) {
-    Con& c = S.con[S.order[n]];
+    Con& k = con_at(S, S.order[n]);
     double q0 = 0, q1 = 0, q2 = 0, UU = 0, UV = 0, VV = 0;
     for (int j = 0; j < 6; j++) {
-      double D = c.D0 * m.dscale[j], ja = c.jar[j], jv = c.jv[j];
+      double D = k.D0 * m.dscale[j], ja = k.jar[j], jv = k.aref[j];
       q0 += 0.5 * D * ja * ja; q1 += D * ja * jv; q2 += 0.5 * D * jv * jv;
       if (j > 0) { double U = ja * m.fr[j - 1], V = jv * m.fr[j - 1]; UU += U * U; UV += U * V; VV += V * V; }
     }
-    c.q0 = q0; c.q1 = q1; c.q2 = q2;
-    c.U0 = c.jar[0] * m.mu; c.V0 = c.jv[0] * m.mu; c.UU = UU; c.UV = UV; c.VV = VV;
+    k.q0 = q0; k.q1 = q1; k.q2 = q2;
+    k.U0 = k.jar[0] * m.mu; k.V0 = k.aref[0] * m.mu; k.UU = UU; k.UV = UV; k.VV = VV;
   }
   WSYNC();
   LsPnt p0, p1, p2, pmid, p1next, p2next;
-  double result;
-  p0.alpha = 0; ls_eval(S, m, lane, L, p0);
-  p1.alpha = p0.alpha - p0.d0 / p0.d1; ls_eval(S, m, lane, L, p1);
+  ls_point(p0, 0.0, S, m, c, lane);
+  ls_point(p1, p0.alpha - tsg_div(p0.d0, p0.d1), S, m, c, lane);
   if (p0.cost < p1.cost) p1 = p0;
-  if (fabs(p1.d0) < gtol) { evals_out = L.evals; return p1.alpha; }
+  if (fabs(p1.d0) < gtol) return p1.alpha;
   int dir = p1.d0 < 0 ? 1 : -1, p2update = 0;
   p2 = p1;
-  while (p1.d0 * dir <= -gtol && L.evals < m.ls_iterations) {
+  TSG_UNROLL1
+  while (p1.d0 * dir <= -gtol && S.ls_evals < m.ls_iterations) {
     p2 = p1; p2update = 1;
-    p1.alpha -= p1.d0 / p1.d1; ls_eval(S, m, lane, L, p1);
-    if (fabs(p1.d0) < gtol) { evals_out = L.evals; return p1.alpha; }
+    ls_point(p1, p1.alpha - tsg_div(p1.d0, p1.d1), S, m, c, lane);
+    if (fabs(p1.d0) < gtol) return p1.alpha;
   }
-  if (L.evals >= m.ls_iterations || !p2update) { evals_out = L.evals; return p1.alpha; }
+  if (S.ls_evals >= m.ls_iterations || !p2update) return p1.alpha;
   p2next = p1;
-  p1next.alpha = p1.alpha - p1.d0 / p1.d1; ls_eval(S, m, lane, L, p1next);
-  bool done = false;
-  result = 0;
-  while (L.evals < m.ls_iterations) {
-    pmid.alpha = 0.5 * (p1.alpha + p2.alpha); ls_eval(S, m, lane, L, pmid);
+  ls_point(p1next, p1.alpha - tsg_div(p1.d0, p1.d1), S, m, c, lane);
+  TSG_UNROLL1
+  while (S.ls_evals < m.ls_iterations) {
+    ls_point(pmid, 0.5 * (p1.alpha + p2.alpha), S, m, c, lane);
     LsPnt cand[3] = {p1next, p2next, pmid};
     int best = -1; double bestcost = 0;
     for (int i = 0; i < 3; i++)
       if (fabs(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
-    if (best >= 0) { result = cand[best].alpha; done = true; break; }
-    int b1 = ls_update_bracket(S, m, lane, L, p1, cand, p1next);
-    int b2 = ls_update_bracket(S, m, lane, L, p2, cand, p2next);
-    if (!b1 && !b2) { result = pmid.alpha; done = true; break; }
+    if (best >= 0) return cand[best].alpha;
+    int b1 = ls_update_bracket(p1, cand, p1next, S, m, c, lane);
+    int b2 = ls_update_bracket(p2, cand, p2next, S, m, c, lane);
+    if (!b1 && !b2) return pmid.alpha;
   }
-  if (!done) {
-    if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
-    else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
-    else result = 0;
-  }
-  evals_out = L.evals;
-  return result;
+  if (p1.cost <= p2.cost && p1.cost < p0.cost) return p1.alpha;
+  if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
+  return 0;
 }
 
 // mj_fwdConstraint: warm-start choice + Newton iterations.  Leaves S.qacc, S.fcon, S.warm.
-TSG_FN void stage_solve(Scratch& S, const DevModel& m, int lane) {
+TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int lane) {
   if (S.nact == 0) {
     LANE_FOR(i, NV) { S.qacc[i] = S.asmooth[i]; S.warm[i] = S.asmooth[i]; S.fcon[i] = 0; }
     WSYNC();
     return;
   }
   // cost at qacc_smooth (Gauss term 0), then at the warm start
-  compute_jar(S, S.asmooth, lane);
-  double cost_sm = constraint_cost(S, m, lane, false);
-  compute_jar(S, S.warm, lane);
-  double cost_ws = constraint_cost(S, m, lane, false) + gauss_cost(S, m, S.warm);
+  compute_jar(VEC_SMOOTH, CTX_ARGS);
+  double cost_sm = total_cost(VEC_SMOOTH, 0, CTX_ARGS);
+  compute_jar(VEC_WARM, CTX_ARGS);
+  double cost_ws = total_cost(VEC_WARM, 0, CTX_ARGS);
   bool use_smooth = cost_ws > cost_sm;
   LANE_FOR(i, NV) S.qacc[i] = use_smooth ? S.asmooth[i] : S.warm[i];
   WSYNC();
-  if (use_smooth) compute_jar(S, S.qacc, lane);
-  double gauss = gauss_cost(S, m, S.qacc);
-  double cost = constraint_cost(S, m, lane, true) + gauss;
-  newton_direction(S, m, lane);
-  double scale = 1 / (m.meaninertia * NV);
+  if (use_smooth) compute_jar(VEC_QACC, CTX_ARGS);
+  double cost = total_cost(VEC_QACC, 1, CTX_ARGS);
+  newton_direction(CTX_ARGS);
+  double scale = tsg_div(1.0, m.meaninertia * NV);
   int iter = 0, nls = 0;
+  TSG_UNROLL1
   while (iter < m.iterations) {
-    int ev;
-    double alpha = line_search(S, m, lane, gauss, ev);
-    nls += ev;
+    double alpha = line_search(CTX_ARGS);
+    nls += S.ls_evals;
     if (alpha == 0) break;
     WSYNC();
     LANE_FOR(i, NV + S.nact * 6) {
       if (i < NV) S.qacc[i] += alpha * S.search[i];
-      else { int n = (i - NV) / 6, r = (i - NV) % 6; Con& c = S.con[S.order[n]]; c.jar[r] += alpha * c.jv[r]; }
+      else { int n = (i - NV) / 6, r = (i - NV) % 6; Con& k = con_at(S, S.order[n]); k.jar[r] += alpha * k.aref[r]; }
     }
     WSYNC();
     double oldcost = cost;
-    gauss = gauss_cost(S, m, S.qacc);
-    cost = constraint_cost(S, m, lane, true) + gauss;
-    newton_direction(S, m, lane);
+    cost = total_cost(VEC_QACC, 1, CTX_ARGS);
+    newton_direction(CTX_ARGS);
     double gn = 0;
+    TSG_UNROLL1
     for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
-    double improvement = scale * (oldcost - cost), gradient = scale * sqrt(gn);
+    double improvement = scale * (oldcost - cost), gradient = scale * tsg_sqrt(gn);
     iter++;
     if (improvement < m.tol || gradient < m.tol) break;
   }
@@ -1186,34 +1291,54 @@ TSG_FN void stage_solve(Scratch& S, const DevModel& m, int lane) {
 // ------------------------------------------------------------------ implicitfast + advance
 TSG_FN void stage_integrate(Scratch& S, const DevModel& m, int lane) {
   double h = m.h;
+  stage_damping_blocks(S, m, lane);
   LANE_FOR(b, NBAR) {
-    double A[21], x[6];
-    for (int r = 0; r < 6; r++)
-      for (int c = 0; c <= r; c++) {
-        int t = r * (r + 1) / 2 + c;
-        A[t] = -h * S.Dblk[b][t] + (r == c ? m.M[6 * b + r] : 0.0);
-      }
-    for (int k = 0; k < 6; k++) x[k] = S.fsm[6 * b + k] + S.fcon[6 * b + k];
+    // (M - h D) x = qfrc_smooth + qfrc_constraint on the bar's 6x6 block, in place in shared memory
+    double* A = S.u.post.Dblk[b];
+    double* x = S.rhs + 6 * b;
+    TSG_UNROLL1
+    for (int t = 0; t < 21; t++) A[t] = -h * A[t];
+    TSG_UNROLL1
+    for (int r = 0; r < 6; r++) { A[r * (r + 1) / 2 + r] += m.M[6 * b + r]; x[r] = S.fsm[6 * b + r] + S.fcon[6 * b + r]; }
+    TSG_UNROLL1
     for (int j = 0; j < 6; j++) {
-      double s = A[j * (j + 1) / 2 + j];
-      for (int k = 0; k < j; k++) s -= A[j * (j + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
-      double piv = sqrt(s);
-      A[j * (j + 1) / 2 + j] = piv;
+      double* Aj = A + j * (j + 1) / 2;
+      double s = Aj[j];
+      TSG_UNROLL1
+      for (int k = 0; k < j; k++) s -= Aj[k] * Aj[k];
+      double inv = tsg_div(1.0, tsg_sqrt(s));
+      Aj[j] = inv;  // store 1 / L_jj
+      TSG_UNROLL1
       for (int i = j + 1; i < 6; i++) {
-        double t = A[i * (i + 1) / 2 + j];
-        for (int k = 0; k < j; k++) t -= A[i * (i + 1) / 2 + k] * A[j * (j + 1) / 2 + k];
-        A[i * (i + 1) / 2 + j] = t / piv;
+        double* Ai = A + i * (i + 1) / 2;
+        double t = Ai[j];
+        TSG_UNROLL1
+        for (int k = 0; k < j; k++) t -= Ai[k] * Aj[k];
+        Ai[j] = t * inv;
       }
     }
-    for (int i = 0; i < 6; i++) { double t = x[i]; for (int k = 0; k < i; k++) t -= A[i * (i + 1) / 2 + k] * x[k]; x[i] = t / A[i * (i + 1) / 2 + i]; }
-    for (int i = 5; i >= 0; i--) { double t = x[i]; for (int k = i + 1; k < 6; k++) t -= A[k * (k + 1) / 2 + i] * x[k]; x[i] = t / A[i * (i + 1) / 2 + i]; }
+    TSG_UNROLL1
+    for (int i = 0; i < 6; i++) {
+      double* Ai = A + i * (i + 1) / 2;
+      double t = x[i];
+      TSG_UNROLL1
+      for (int k = 0; k < i; k++) t -= Ai[k] * x[k];
+      x[i] = t * Ai[i];
+    }
+    TSG_UNROLL1
+    for (int i = 5; i >= 0; i--) {
+      double t = x[i];
+      TSG_UNROLL1
+      for (int k = i + 1; k < 6; k++) t -= A[k * (k + 1) / 2 + i] * x[k];
+      x[i] = t * A[i * (i + 1) / 2 + i];
+    }
     double* v = S.qvel + 6 * b; double* q = S.qpos + 7 * b;
     for (int k = 0; k < 6; k++) v[k] += h * x[k];
     for (int k = 0; k < 3; k++) q[k] += h * v[k];
     double ax[3] = {v[3], v[4], v[5]}, qr[4], qn[4];
     double ang = h * normalize3(ax);
     if (ang == 0) { qr[0] = 1; qr[1] = qr[2] = qr[3] = 0; }
-    else { double s = sin(ang * 0.5); qr[0] = cos(ang * 0.5); qr[1] = ax[0] * s; qr[2] = ax[1] * s; qr[3] = ax[2] * s; }
+    else { double sn, cs; sincos(ang * 0.5, &sn, &cs); qr[0] = cs; qr[1] = ax[0] * sn; qr[2] = ax[1] * sn; qr[3] = ax[2] * sn; }
     normalize4(q + 3);
     const double* a = q + 3;
     qn[0] = a[0] * qr[0] - a[1] * qr[1] - a[2] * qr[2] - a[3] * qr[3];
@@ -1239,7 +1364,7 @@ TSG_FN_NOINLINE void forward(CTX_PARAMS) {
   stage_tendon(S, m, lane);
   stage_smooth(S, m, lane);
   stage_constraint(S, m, lane);
-  stage_solve(S, m, lane);
+  stage_solve(S, m, c, lane);
 }
 // one mj_step
 TSG_FN_NOINLINE void substep(CTX_PARAMS) {
@@ -1270,7 +1395,7 @@ TSG_FN void stage_cfrc(Scratch& S, const DevModel& m, int lane) {
     } else copy3(com, S.xstale + 3 * (body - 1));
     double acc = 0;
     for (int n = 0; n < S.nact; n++) {
-      const Con& c = S.con[S.order[n]];
+      const Con& c = con_at(S, S.order[n]);
       double s;
       if (c.b2 == body - 1) s = 1; else if (c.b1 == body - 1) s = -1; else continue;
       double F[3], T[3];
@@ -1278,7 +1403,7 @@ TSG_FN void stage_cfrc(Scratch& S, const DevModel& m, int lane) {
       if (comp >= 3) acc += s * F[comp - 3];
       else { double r[3], tq[3]; sub3(r, c.pos, com); cross3(tq, r, F); acc += s * (tq[comp] + T[comp]); }
     }
-    S.cfrc[body][comp] = acc;
+    S.u.post.cfrc[body][comp] = acc;
   }
   WSYNC();
 }

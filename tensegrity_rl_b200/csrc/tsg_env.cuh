@@ -15,6 +15,7 @@ struct Aux {  // warp-uniform env bookkeeping kept in registers
   double xy_prev[2], psi_prev, reset_psi, waypt[2], ori[2];
   double step_num, ep_ret, ep_len, xvel, yvel;
   int head_n, head_pos;
+  double* heading;  // [HEADING_SLOTS] in global memory
 };
 struct StepOut {  // warp-uniform results of one env step
   double reward, fwd, ctrl_cost, healthy, psi, xy[2];
@@ -34,23 +35,23 @@ TSG_FN void read_pose(const Scratch& S, Pose& P) {
   P.xy[0] = (S.xstale[0] + S.xstale[3] + S.xstale[6]) / 3;
   P.xy[1] = (S.xstale[1] + S.xstale[4] + S.xstale[7]) / 3;
   for (int k = 0; k < 3; k++) {
-    P.left[k] = (S.gpos[3 * 1 + k] + S.gpos[3 * 6 + k] + S.gpos[3 * 11 + k]) / 3;   // s0, s2, s4
-    P.right[k] = (S.gpos[3 * 2 + k] + S.gpos[3 * 7 + k] + S.gpos[3 * 12 + k]) / 3;  // s1, s3, s5
+    P.left[k] = (S.sph[3 * 0 + k] + S.sph[3 * 2 + k] + S.sph[3 * 4 + k]) / 3;   // s0, s2, s4
+    P.right[k] = (S.sph[3 * 1 + k] + S.sph[3 * 3 + k] + S.sph[3 * 5 + k]) / 3;  // s1, s3, s5
   }
   P.psi = atan2(-(P.left[0] - P.right[0]), P.left[1] - P.right[1]);
 }
 
 TSG_FN double ditch_reward(const EnvCfg& c, const Aux& A, const double* xy) {  // tr_env.py:656-667
   double pv[2] = {A.waypt[0] - A.ori[0], A.waypt[1] - A.ori[1]};
-  double dp = sqrt(pv[0] * pv[0] + pv[1] * pv[1]);
+  double dp = tsg_sqrt(pv[0] * pv[0] + pv[1] * pv[1]);
   double pn[2] = {pv[0] / dp, pv[1] / dp};
   double tv[2] = {A.waypt[0] - xy[0], A.waypt[1] - xy[1]};
   double along = tv[0] * pn[0] + tv[1] * pn[1];
   double bx = tv[0] - along * pn[0], by = tv[1] - along * pn[1];
-  double bias = sqrt(bx * bx + by * by);
+  double bias = tsg_sqrt(bx * bx + by * by);
   double ditch = c.ditch_reward_max * (1.0 - fabs(along) / dp) * exp(-(bias * bias) / (2 * c.ditch_reward_stdev * c.ditch_reward_stdev));
   double dx = xy[0] - A.waypt[0], dy = xy[1] - A.waypt[1];
-  double dn = sqrt(dx * dx + dy * dy);
+  double dn = tsg_sqrt(dx * dx + dy * dy);
   double wp = c.waypt_reward_amplitude * exp(-(dn * dn) / (2 * c.waypt_reward_stdev * c.waypt_reward_stdev));
   return ditch + wp;
 }
@@ -70,7 +71,7 @@ TSG_FN void mat2quat_scipy(const double* M, double* q) {
   } else {
     q[0] = M[7] - M[5]; q[1] = M[2] - M[6]; q[2] = M[3] - M[1]; q[3] = 1 + tr;
   }
-  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double n = tsg_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   for (int i = 0; i < 4; i++) q[i] /= n;
 }
 
@@ -83,35 +84,35 @@ TSG_FN void compute_obs(EnvScratch& S, const DevModel& m, const EnvCfg& c, const
           int b = i / 4; const double* R = S.xmat + 9 * b;
           double G[9] = {-R[0], -R[1], R[2], -R[3], -R[4], R[5], -R[6], -R[7], R[8]}, q[4];
           mat2quat_scipy(G, q);
-          for (int k = 0; k < 4; k++) S.obs[i + k] = q[k];
+          for (int k = 0; k < 4; k++) S.u.post.obs[i + k] = q[k];
         }
-      } else if (i < 30) S.obs[i] = S.qvel[i - 12];
-      else S.obs[i] = S.tlen[i - 30];
+      } else if (i < 30) S.u.post.obs[i] = S.qvel[i - 12];
+      else S.u.post.obs[i] = S.tlen[i - 30];
     }
     WSYNC();
     return;
   }
   double cen[3] = {0, 0, 0};
   for (int b = 0; b < NBAR; b++)
-    for (int k = 0; k < 3; k++) cen[k] += S.gpos[3 * (5 * b + 1) + k] + S.gpos[3 * (5 * b + 2) + k];
+    for (int k = 0; k < 3; k++) cen[k] += S.sph[3 * (2 * b) + k] + S.sph[3 * (2 * b + 1) + k];
   for (int k = 0; k < 3; k++) cen[k] /= 6;
   int nvel = c.use_cap_velocity ? 18 : 0;
   LANE_FOR(i, 18 + nvel + 9) {
-    if (i < 18) { int cap = i / 3, k = i % 3, g = 5 * (cap / 2) + 1 + (cap % 2); S.obs[i] = S.gpos[3 * g + k] - cen[k]; }
+    if (i < 18) { int cap = i / 3, k = i % 3; S.u.post.obs[i] = S.sph[3 * cap + k] - cen[k]; }
     else if (i < 18 + nvel) {
-      int j = i - 18, cap = j / 3, k = j % 3, b = cap / 2, g = 5 * b + 1 + (cap % 2);
+      int j = i - 18, cap = j / 3, k = j % 3, b = cap / 2;
       double r[3], w[3] = {S.qvel[6 * b + 3], S.qvel[6 * b + 4], S.qvel[6 * b + 5]}, cr[3];
-      sub3(r, S.gpos + 3 * g, S.xstale + 3 * b);
+      sub3(r, S.sph + 3 * cap, S.xstale + 3 * b);
       cross3(cr, w, r);  // local-frame angular velocity used as if world-frame (tr_env.py:599-604)
-      S.obs[i] = S.qvel[6 * b + k] + cr[k];
-    } else S.obs[i] = S.tlen[i - 18 - nvel];
+      S.u.post.obs[i] = S.qvel[6 * b + k] + cr[k];
+    } else S.u.post.obs[i] = S.tlen[i - 18 - nvel];
   }
   int base = 27 + nvel;
   if (c.task == TASK_TRACKING || c.task == TASK_AIMING) {
-    double tx = A.waypt[0] - cen[0], ty = A.waypt[1] - cen[1], n = sqrt(tx * tx + ty * ty);
-    if (lane == 0) { S.obs[base] = tx; S.obs[base + 1] = ty; S.obs[base + 2] = atan2(ty / n, tx / n); }
+    double tx = A.waypt[0] - cen[0], ty = A.waypt[1] - cen[1], n = tsg_sqrt(tx * tx + ty * ty);
+    if (lane == 0) { S.u.post.obs[base] = tx; S.u.post.obs[base + 1] = ty; S.u.post.obs[base + 2] = atan2(ty / n, tx / n); }
   } else if (c.task == TASK_VEL_TRACK) {
-    if (lane == 0) { S.obs[base] = 0.5 * cos(A.reset_psi); S.obs[base + 1] = 0.5 * sin(A.reset_psi); S.obs[base + 2] = 0.0; }
+    if (lane == 0) { S.u.post.obs[base] = 0.5 * cos(A.reset_psi); S.u.post.obs[base + 1] = 0.5 * sin(A.reset_psi); S.u.post.obs[base + 2] = 0.0; }
   }
   WSYNC();
 }
@@ -123,13 +124,14 @@ TSG_FN_NOINLINE void simulate(CTX_PARAMS) {
   stage_cfrc(S, m, lane);
 }
 
-TSG_FN void heading_push(EnvScratch& S, Aux& A, double v, int lane) {
-  if (lane == 0) S.heading[(A.head_pos + A.head_n) % HEADING_SLOTS] = v;
+// heading ring buffer (the reference's deque, never cleared across episodes) lives in global memory
+TSG_FN void heading_push(Aux& A, double v, int lane) {
+  if (lane == 0) A.heading[(A.head_pos + A.head_n) % HEADING_SLOTS] = v;
   A.head_n++;
   WSYNC();
 }
-TSG_FN double heading_pop(EnvScratch& S, Aux& A) {
-  double v = S.heading[A.head_pos];
+TSG_FN double heading_pop(Aux& A) {
+  double v = A.heading[A.head_pos];
   A.head_pos = (A.head_pos + 1) % HEADING_SLOTS;
   A.head_n--;
   return v;
@@ -176,9 +178,9 @@ TSG_FN_NOINLINE void env_step(Aux& A, StepOut& O, CTX_PARAMS) {
   bool extra_term = false;
   if (c.task == TASK_TURN) {
     is_healthy = healthy_turn;
-    heading_push(S, A, psi_after, lane);
+    heading_push(A, psi_after, lane);
     if (A.head_n > delay) {
-      double old_psi = heading_pop(S, A), pa = psi_after;
+      double old_psi = heading_pop(A), pa = psi_after;
       if (pa < -PI / 2 && old_psi > PI / 2) pa = 2 * PI + pa;
       else if (pa > PI / 2 && old_psi < -PI / 2) pa = -2 * PI + pa;
       if (c.env_kind == ENV_TR) psi_info = pa;  // tr_env rebinds psi_after, legacy too
@@ -188,15 +190,15 @@ TSG_FN_NOINLINE void env_step(Aux& A, StepOut& O, CTX_PARAMS) {
   } else if (c.task == TASK_STRAIGHT) {
     double dx = P.xy[0] - xy_before[0], dy = P.xy[1] - xy_before[1];
     double psi_diff = fabs(atan2(dy, dx) - A.reset_psi);
-    fwd = c.desired_direction * (sqrt(dx * dx + dy * dy) * cos(psi_diff) / dt);
+    fwd = c.desired_direction * (tsg_sqrt(dx * dx + dy * dy) * cos(psi_diff) / dt);
   } else if (c.task == TASK_AIMING) {
     is_healthy = healthy_turn;
-    double tx = A.waypt[0] - xy_before[0], ty = A.waypt[1] - xy_before[1], n = sqrt(tx * tx + ty * ty);
+    double tx = A.waypt[0] - xy_before[0], ty = A.waypt[1] - xy_before[1], n = tsg_sqrt(tx * tx + ty * ty);
     double target_psi = atan2(ty / n, tx / n);
     double newp = angle_normalize(target_psi - psi_after);
-    heading_push(S, A, newp, lane);
+    heading_push(A, newp, lane);
     if (A.head_n > delay) {
-      double oldp = heading_pop(S, A);
+      double oldp = heading_pop(A);
       fwd = -(fabs(newp) - fabs(oldp)) / (dt * delay) * c.yaw_reward_weight;
     }
     healthy = 0;
@@ -208,18 +210,18 @@ TSG_FN_NOINLINE void env_step(Aux& A, StepOut& O, CTX_PARAMS) {
   } else {  // vel_track, tr_env.py:461-474, 669-678
     double ang = angle_normalize(psi_after - psi_before) / dt;
     double cx = 0.5 * cos(A.reset_psi), cy = 0.5 * sin(A.reset_psi);
-    double le = sqrt((xvel - cx) * (xvel - cx) + (yvel - cy) * (yvel - cy)), ae = ang - 0.0;
+    double le = tsg_sqrt((xvel - cx) * (xvel - cx) + (yvel - cy) * (yvel - cy)), ae = ang - 0.0;
     fwd = 1.0 * exp(-5.0 * le * le) + 0.5 * exp(-7.0 * ae * ae);
   }
   bool terminated = c.terminate_when_unhealthy ? !is_healthy : false;
   if (extra_term) terminated = true;
   double maxc = 0;
-  for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs(S.cfrc[i / 6][i % 6]));
+  for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs(S.u.post.cfrc[i / 6][i % 6]));
   if (maxc > c.kill_force) terminated = true;  // tr_env.py:480-481
   double barf = 0;  // run.py:155-161 total bar-bar contact force magnitude
   for (int n = 0; n < S.nact; n++) {
-    const Con& k = S.con[S.order[n]];
-    if (k.b1 >= 0) barf += sqrt(k.force[0] * k.force[0] + k.force[1] * k.force[1] + k.force[2] * k.force[2]);
+    const Con& k = con_at(S, S.order[n]);
+    if (k.b1 >= 0) barf += tsg_sqrt(k.force[0] * k.force[0] + k.force[1] * k.force[1] + k.force[2] * k.force[2]);
   }
   O.reward = fwd + healthy - ctrl_cost;
   O.fwd = fwd; O.ctrl_cost = ctrl_cost; O.healthy = healthy; O.psi = psi_info;
@@ -257,7 +259,7 @@ TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A,
     for (int k = 0; k < 7; k++) p[k] = c.reset_pose[idx][7 * b + k];
     double* q = S.qpos + 7 * b;
     q[0] = ct * p[0] - st * p[1]; q[1] = st * p[0] + ct * p[1]; q[2] = p[2];
-    double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
+    double n = tsg_sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
     double w = p[3] / n, x = p[4] / n, y = p[5] / n, z = p[6] / n;
     q[3] = ch * w - sh * z; q[4] = ch * x - sh * y; q[5] = ch * y + sh * x; q[6] = ch * z + sh * w;  // q_z(theta) * q
   }
@@ -314,7 +316,7 @@ TSG_FN void load_env(EnvScratch& S, Aux& A, const double* rec, const double* hea
     else if (i < SO_ACT) S.ctrl[i - SO_CTRL] = v;
     else S.act[i - SO_ACT] = v;
   }
-  if (need_head) { LANE_FOR(i, HEADING_SLOTS) S.heading[i] = head[i]; }
+  A.heading = const_cast<double*>(head);
   A.xy_prev[0] = rec[SO_XY_PREV]; A.xy_prev[1] = rec[SO_XY_PREV + 1]; A.psi_prev = rec[SO_PSI_PREV];
   A.reset_psi = rec[SO_RESET_PSI]; A.waypt[0] = rec[SO_WAYPT]; A.waypt[1] = rec[SO_WAYPT + 1];
   A.ori[0] = rec[SO_ORI]; A.ori[1] = rec[SO_ORI + 1];
@@ -334,7 +336,6 @@ TSG_FN void store_env(const EnvScratch& S, const Aux& A, double* rec, double* he
     else v = S.act[i - SO_ACT];
     rec[i] = v;
   }
-  if (need_head) { LANE_FOR(i, HEADING_SLOTS) head[i] = S.heading[i]; }
   if (lane == 0) {
     rec[SO_XY_PREV] = A.xy_prev[0]; rec[SO_XY_PREV + 1] = A.xy_prev[1]; rec[SO_PSI_PREV] = A.psi_prev;
     rec[SO_RESET_PSI] = A.reset_psi; rec[SO_WAYPT] = A.waypt[0]; rec[SO_WAYPT + 1] = A.waypt[1];
@@ -365,8 +366,8 @@ struct StepIO {
 };
 
 TSG_FN void write_obs(const EnvScratch& S, const EnvCfg& c, const StepIO& io, int e, int lane) {
-  if (io.obs) { LANE_FOR(i, c.obs_dim) io.obs[(size_t)e * c.obs_dim + i] = S.obs[i]; }
-  if (io.obs32) { LANE_FOR(i, c.obs_dim) io.obs32[(size_t)e * c.obs_dim + i] = (float)S.obs[i]; }
+  if (io.obs) { LANE_FOR(i, c.obs_dim) io.obs[(size_t)e * c.obs_dim + i] = S.u.post.obs[i]; }
+  if (io.obs32) { LANE_FOR(i, c.obs_dim) io.obs32[(size_t)e * c.obs_dim + i] = (float)S.u.post.obs[i]; }
 }
 
 // the body of the step kernel for env e
@@ -446,7 +447,7 @@ TSG_FN void make_draws(double* d, unsigned long long seed, unsigned long long en
   d[0] = un[0]; d[1] = un[1]; d[8] = un[2]; d[9] = un[3];
   for (int k = 0; k < 3; k++) {  // Box-Muller
     double u1 = 1.0 - un[4 + 2 * k], u2 = un[5 + 2 * k];
-    double r = sqrt(-2.0 * log(u1));
+    double r = tsg_sqrt(-2.0 * log(u1));
     d[2 + 2 * k] = r * cos(2 * PI * u2); d[3 + 2 * k] = r * sin(2 * PI * u2);
   }
 }

@@ -71,12 +71,15 @@ inline std::string make_dev_model(const TsgModel& t, DevModel& m, const float* h
   m.K = -t.solref[0] / (dmax * dmax); m.B = -t.solref[1] / dmax;
   for (int k = 0; k < 5; k++) { m.solimp[k] = t.solimp[k]; m.fr[k] = t.friction[k]; }
   m.mu = t.friction[0] / sqrt(t.impratio);
+  m.inv_mu2 = 1.0 / (m.mu * m.mu * (1 + m.mu * m.mu));
   m.dscale[0] = 1; m.fscale[0] = m.mu;
   for (int j = 1; j < 6; j++) {
     // R_j = (R_0 / impratio) * f0^2 / f_{j-1}^2  ->  D_j = D_0 * dscale_j
     m.dscale[j] = t.impratio * (t.friction[j - 1] * t.friction[j - 1]) / (t.friction[0] * t.friction[0]);
     m.fscale[j] = t.friction[j - 1];
   }
+  for (int r = 0; r < 6; r++) { m.wtab[0][r] = m.dscale[r]; m.wtab[1][r] = r ? t.friction[r - 1] * t.friction[r - 1] : 0.0; }
+  for (int i = 0, e = 0; i < NV; i++) for (int j = 0; j <= i; j++, e++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; }
   m.floor_type = t.floor_type;
   for (int k = 0; k < 3; k++) { m.fpos[k] = t.floor_pos[k]; m.fnormal[k] = t.floor_mat[3 * k + 2]; }
   if (t.floor_type == TSG_FLOOR_HFIELD) {

@@ -29,7 +29,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    so = _build.SO
+    so = os.environ.get("TSG_LIB", _build.SO)  # alternative builds for A/B measurements
     if not os.path.isfile(so):
         raise TsgError(f"{so} not built: run `python -m tensegrity_rl_b200.build` (needs nvcc); "
                        "there is no CPU fallback")

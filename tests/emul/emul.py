@@ -9,22 +9,23 @@ from tensegrity_rl_b200 import model as M
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 STATE_STRIDE, INFO_DIM, HEADING_SLOTS, NDRAW = 96, 32, 32, 10
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        so = os.path.join(HERE, "libtsg_emul.so")
+def lib(reverse=False):
+    """reverse=True: the variant that runs the items of every phase in reverse order (hazard detector)."""
+    if reverse not in _libs:
+        so = os.path.join(HERE, "libtsg_emul_rev.so" if reverse else "libtsg_emul.so")
         csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "tensegrity_rl_b200", "csrc")
         deps = [os.path.join(HERE, "tsg_emul.cpp")] + [os.path.join(csrc, f) for f in ("tsg_core.cuh", "tsg_env.cuh", "tsg_host.h")]
         if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",
-                                   "-o", so, os.path.join(HERE, "tsg_emul.cpp")])
+                                   "-Wno-unknown-pragmas"] + (["-DTSG_EMUL_REVERSE"] if reverse else []) +
+                                  ["-o", so, os.path.join(HERE, "tsg_emul.cpp")])
         L = C.CDLL(so)
         L.emul_create.restype = C.c_char_p
-        _lib = L
-    return _lib
+        _libs[reverse] = L
+    return _libs[reverse]
 
 
 def P(a, t=C.c_double):
@@ -32,11 +33,11 @@ def P(a, t=C.c_double):
 
 
 class Emul:
-    def __init__(self, xml_file="flat", **env_kwargs):
+    def __init__(self, xml_file="flat", reverse=False, **env_kwargs):
         self.md = M.load_model(xml_file)
         self.model, self._keep = M.model_struct(self.md)
         self.cfg = M.env_config(self.md, **env_kwargs)
-        self.L = lib()
+        self.L = lib(reverse)
         h = C.c_void_p()
         err = self.L.emul_create(C.byref(self.model), C.byref(self.cfg), C.byref(h))
         if err:

@@ -14,6 +14,7 @@ struct Emul {
   EnvCfg c;
   float* hdata;
   EnvScratch S;
+  Con spill[MAXC - MAXC_S];
 };
 
 extern "C" {
@@ -31,6 +32,7 @@ const char* emul_create(const TsgModel* model, const TsgEnvConfig* cfg, void** o
   if (err.empty()) err = make_env_cfg(*cfg, *model, E->c);
   if (!err.empty()) { delete E; return err.c_str(); }
   memset(&E->S, 0, sizeof(E->S));
+  E->S.spill = E->spill;
   *out = E;
   return nullptr;
 }
@@ -74,7 +76,7 @@ void emul_mj_step(void* h, double* rec, const double* ctrl, int nstep, double* t
   for (int s = 0; s < nstep; s++) substep(E->S, E->m, E->c, 0);
   stage_cfrc(E->S, E->m, 0);
   if (ten_length) for (int i = 0; i < NTEN; i++) ten_length[i] = E->S.tlen[i];
-  if (cfrc_ext) for (int i = 0; i < 24; i++) cfrc_ext[i] = E->S.cfrc[i / 6][i % 6];
+  if (cfrc_ext) for (int i = 0; i < 24; i++) cfrc_ext[i] = E->S.u.post.cfrc[i / 6][i % 6];
   if (stats) { stats[0] = E->S.nact; stats[1] = E->S.niter_total; stats[2] = E->S.nls_total; stats[3] = E->S.nmpr_total; stats[4] = E->S.overflow; stats[5] = E->S.bad; }
   store_env(E->S, A, rec, heading, false, 0);
 }

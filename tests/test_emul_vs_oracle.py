@@ -14,10 +14,13 @@ def _copy_state(mj, em):
     em.rec[63:69] = mj.act
 
 
+@pytest.mark.parametrize("reverse", [False, True])
 @pytest.mark.parametrize("model,lo,hi", [("flat", -0.45, -0.15), ("flat", -0.45, 0.15), ("uneven", -0.45, 0.15)])
-def test_single_step_state_parity(oracle, model, lo, hi):
-    """one env step (20 substeps) from identical (qpos, qvel, act, warmstart, ctrl): 1e-9 relative."""
-    mj, em = oracle.MjLike(model), E.Emul(model)
+def test_single_step_state_parity(oracle, model, lo, hi, reverse):
+    """one env step (20 substeps) from identical (qpos, qvel, act, warmstart, ctrl): 1e-9 relative.
+    reverse=True runs the items of every lane loop in reverse order: a phase whose result depends on the item
+    order (an intra-phase read/write hazard that would be a race on the GPU) fails here."""
+    mj, em = oracle.MjLike(model), E.Emul(model, reverse=reverse)
     rng = np.random.default_rng(5)
     worst = 0.0
     for st in range(60):
@@ -37,7 +40,7 @@ def test_single_step_state_parity(oracle, model, lo, hi):
 def test_conservative_prefilter_matches_unfiltered_oracle(oracle):
     """the CUDA source filters bar-bar pairs with an analytic capsule bound before MPR; the oracle runs MPR on
     every pair that passes MuJoCo's bounding-sphere test.  Squeeze the bars together and compare."""
-    mj, em = oracle.MjLike("flat"), E.Emul("flat")
+    mj, em = oracle.MjLike("flat"), E.Emul("flat", reverse=True)
     rng = np.random.default_rng(7)
     nbar = 0
     for st in range(80):
@@ -61,7 +64,7 @@ CASES = [("flat", "tr_env", "straight"), ("flat", "tr_env", "turn"), ("flat", "t
 def test_env_semantics_parity(xml, kind, task):
     rng = np.random.default_rng(11)
     oe = OracleEnv(xml, kind, desired_action=task)
-    em = E.Emul(xml, env_kind=kind, desired_action=task)
+    em = E.Emul(xml, env_kind=kind, desired_action=task, reverse=(task in ("turn", "tracking")))
     draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
     o1, o2 = oe.reset(draws), em.reset(draws)
     assert o1.shape == o2.shape == (oe.cfg.obs_dim,)
@@ -98,3 +101,20 @@ def test_philox_draws_are_keyed_by_env_and_reset_count():
     assert (u[:, [0, 1, 8, 9]] >= 0).all() and (u[:, [0, 1, 8, 9]] < 1).all()
     assert abs(u[:, [0, 1, 8, 9]].mean() - 0.5) < 0.02
     assert abs(u[:, 2:8].mean()) < 0.03 and abs(u[:, 2:8].std() - 1) < 0.03
+
+
+def test_contact_spill_path(oracle):
+    """two bars pressed flat into the floor: 19 contacts, i.e. 13 beyond the shared-memory slots (MAXC_S = 6)
+    that live in the per-warp spill area; results must still match the dense oracle."""
+    mj, em = oracle.MjLike("flat"), E.Emul("flat", reverse=True)
+    q = []
+    for b in range(3):
+        q += [0.0, 0.4 * b, 0.0375, np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0] if b < 2 else [0.0, 0.8, 3.0, 1, 0, 0, 0]
+    mj.reset_data(); mj.qpos[:] = q; mj.ctrl[:] = 0.15
+    for st in range(2):
+        em.rec[0:21] = mj.qpos; em.rec[21:39] = mj.qvel; em.rec[39:57] = mj.qacc_warmstart
+        mj.step(1)
+        ten, cfrc, stats = em.mj_step(np.full(6, 0.15), 1)
+        assert stats[0] == mj.nefc // 6 == 19 and stats[4] == 0
+        assert np.abs(em.qvel - mj.qvel).max() < 1e-10
+        assert np.abs(em.warm - mj.qacc_warmstart).max() <= 1e-9 * np.abs(mj.qacc_warmstart).max()

@@ -202,7 +202,8 @@ def test_properties_at_scale(xml, n):
     assert np.abs(obs[:, :18].reshape(n, 6, 3).sum(1)).max() < 1e-9        # cap positions are centroid-relative
     caps = obs[:, :18].reshape(n, 6, 3)
     assert np.abs(np.linalg.norm(caps[:, 0::2] - caps[:, 1::2], axis=2) - 1.376).max() < 1e-9  # rigid bars
-    assert np.array_equal(obs[:, 36:45], info[:, 8:17])                       # tendon lengths in obs == info
+    keep = ~done.cpu().numpy().astype(bool)                                   # auto-reset rows hold the new episode's obs
+    assert np.array_equal(obs[keep, 36:45], info[keep, 8:17])                 # tendon lengths in obs == info
     assert info[:, 28].sum() == 0 and info[:, 29].sum() == 0                  # no contact overflow, no bad state
     assert 0.5 < info[:, 19].mean() < 8                                        # contacts per env
     v.close()
