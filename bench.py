@@ -190,7 +190,7 @@ def main():
         return ms, env.launches - l0, stats
 
     env = TensegrityVecEnv(n, xml_file="flat", env="tr_env", device=local_rank, seed=0, env_id_base=rank * n,
-                           auto_reset=True, desired_action="straight")
+                           auto_reset=True, desired_action="straight", reset_pool="auto")
     env.reset_tensor()
     torch.cuda.synchronize()
     state_bytes = n * (96 * 8 + env.obs_dim * 8 + 6 * 8)
@@ -249,7 +249,7 @@ def main():
         for s in [int(x) for x in args.sweep.split(",") if x]:
             if s == n:
                 continue
-            e2 = TensegrityVecEnv(s, xml_file="flat", env="tr_env", device=local_rank, seed=0, auto_reset=True)
+            e2 = TensegrityVecEnv(s, xml_file="flat", env="tr_env", device=local_rank, seed=0, auto_reset=True, reset_pool="auto")
             e2.reset_tensor()
             m2, _, _ = timed_run(e2, s, 10, 3, True)
             sweep[str(s)] = s * 10 / (m2 * 1e-3)
@@ -275,7 +275,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "flat_random_ctrl_fp64: 3prism_jonathan_steady_side.xml, tr_env straight, ctrl~U[-0.45,-0.15], "
                                    "%d envs/GPU (BASELINE configs[1] inputs at the configs[4] per-GPU env count)" % n,
-                       "envs_per_gpu": n, "frame_skip": 20, "obs_dim": obs_dim, "auto_reset": True,
+                       "envs_per_gpu": n, "frame_skip": 20, "obs_dim": obs_dim, "auto_reset": True, "reset_pool_slots": env.reset_pool,
                        "l2": "flush between timed steps" if flush else "state+obs working set %.0f MB > 126 MB L2" % (state_bytes / 2 ** 20),
                        "done_fraction_per_step": done_frac, "mean_contacts": ncon, "newton_iters_per_substep": niter,
                        "linesearch_evals_per_substep": nls, "contact_overflow": overflow, "bad_state": bad,

@@ -71,6 +71,14 @@ int tsg_device_count(void);
 /* n_envs independent envs on CUDA device `device`; env_id_base offsets the RNG stream ids (rank sharding) */
 int tsg_create(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int device, long long env_id_base,
                TsgHandle **out);
+/* same, with n_pool background reset slots: every tsg_step(auto_reset=1) launch also advances each not-yet-ready
+ * slot by one of the reset's 50 warm-up env steps, and envs that are done receive a ready slot (state, heading ring,
+ * reset observation) instead of resetting synchronously -- the 1000-substep reset latency leaves the step path.
+ * Done envs that find no ready slot fall back to the synchronous reset.  tsg_reset(mask = NULL) prewarms all slots. */
+int tsg_create_pooled(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int n_pool, int device,
+                      long long env_id_base, TsgHandle **out);
+/* counts3 = {done envs, ready slots, slots handed out} of the last auto-reset (synchronous read) */
+int tsg_pool_stats_host(TsgHandle *h, int *counts3);
 int tsg_destroy(TsgHandle *h);
 int tsg_num_envs(const TsgHandle *h);
 int tsg_obs_dim(const TsgHandle *h);

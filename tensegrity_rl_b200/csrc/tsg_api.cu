@@ -51,16 +51,75 @@ __global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(c
   EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
   if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * TSG_WARPS + warp) * (MAXC - MAXC_S);
   __syncwarp();
+  // items: the n_envs envs, then (STEP: every launch, RESET of all envs: prewarm) the background reset pool slots
+  int n_items = io.n_envs + ((MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? io.n_pool : 0);
   for (;;) {
     int e = 0;
     if (lane == 0) e = atomicAdd(counter, 1);
     e = __shfl_sync(0xffffffffu, e, 0);
-    if (e >= io.n_envs) break;
+    if (e >= n_items) break;
+    if (e >= io.n_envs) { run_pool(S, m, c, io, e - io.n_envs, MODE == MODE_RESET, lane); __syncwarp(); continue; }
     if (MODE == MODE_RESET && io.mask && !io.mask[e]) continue;
     if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
     else if (MODE == MODE_RESET) run_reset(S, m, c, io, e, lane);
     else run_forward(S, m, c, io, e, lane);
     __syncwarp();
+  }
+}
+
+// Hand ready pool slots to envs that are done (one CTA; ordered, hence deterministic: the k-th done env gets the
+// k-th ready slot).  Copies record (all but the env's own reset counter), heading ring and reset observation;
+// the slot restarts from phase 0 with its next draw.  Done envs left without a slot are flagged in need_sync.
+__global__ void __launch_bounds__(1024) tsg_assign_kernel(double* __restrict__ state, double* __restrict__ heading,
+                                                           const uint8_t* __restrict__ done, uint8_t* __restrict__ need_sync,
+                                                           double* obs, float* obs32, double* term_obs,
+                                                           const double* __restrict__ pool_obs, int* __restrict__ lists,
+                                                           int* __restrict__ counts, int n, int n_pool, int obs_dim, int ready_phase) {
+  __shared__ int wcount[32], woff[32], s_ndone, s_nready;
+  int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* done_list = lists;            // first n_pool done envs, in env order
+  int* ready_list = lists + n_pool;  // ready pool slots, in slot order
+  for (int pass = 0; pass < 2; pass++) {  // pass 0: done envs, pass 1: ready slots
+    int total = pass == 0 ? n : n_pool;
+    int seg = ((total + 31) / 32 + 31) / 32 * 32, lo = warp * seg, hi = min(total, lo + seg);
+    int cnt = 0;
+    for (int b = lo; b < hi; b += 32) {
+      int i = b + lane;
+      bool f = i < hi && (pass == 0 ? done[i] != 0 : (int)state[(size_t)(n + i) * STATE_STRIDE + SO_FLAGS] == ready_phase);
+      cnt += __popc(__ballot_sync(0xffffffffu, f));
+    }
+    if (lane == 0) wcount[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) { int s = 0; for (int w = 0; w < 32; w++) { woff[w] = s; s += wcount[w]; } if (pass == 0) s_ndone = s; else s_nready = s; }
+    __syncthreads();
+    int off = woff[warp];
+    int* out = pass == 0 ? done_list : ready_list;
+    for (int b = lo; b < hi; b += 32) {
+      int i = b + lane;
+      bool f = i < hi && (pass == 0 ? done[i] != 0 : (int)state[(size_t)(n + i) * STATE_STRIDE + SO_FLAGS] == ready_phase);
+      unsigned mk = __ballot_sync(0xffffffffu, f);
+      int k = off + __popc(mk & ((1u << lane) - 1));
+      if (f && k < n_pool) out[k] = i;
+      off += __popc(mk);
+    }
+    __syncthreads();
+  }
+  int npair = min(min(s_ndone, s_nready), n_pool);
+  if (tid == 0) { counts[0] = s_ndone; counts[1] = s_nready; counts[2] = npair; }
+  if (need_sync) for (int i = tid; i < n; i += blockDim.x) need_sync[i] = done[i];
+  __syncthreads();
+  for (int k = warp; k < npair; k += 32) {
+    int e = done_list[k], p = ready_list[k];
+    double* dst = state + (size_t)e * STATE_STRIDE;
+    double* src = state + (size_t)(n + p) * STATE_STRIDE;
+    for (int i = lane; i < STATE_STRIDE; i += 32) if (i != SO_NRESET && i != SO_FLAGS) dst[i] = src[i];
+    for (int i = lane; i < HEADING_SLOTS; i += 32) heading[(size_t)e * HEADING_SLOTS + i] = heading[(size_t)(n + p) * HEADING_SLOTS + i];
+    for (int i = lane; i < obs_dim; i += 32) {
+      double v = pool_obs[(size_t)p * obs_dim + i];
+      if (obs) { if (term_obs) term_obs[(size_t)e * obs_dim + i] = obs[(size_t)e * obs_dim + i]; obs[(size_t)e * obs_dim + i] = v; }
+      if (obs32) obs32[(size_t)e * obs_dim + i] = (float)v;
+    }
+    if (lane == 0) { src[SO_FLAGS] = 0; src[SO_NRESET] += 1; if (need_sync) need_sync[e] = 0; }
   }
 }
 
@@ -87,7 +146,7 @@ __global__ void tsg_scatter_kernel(double* __restrict__ state, int n, const doub
   if (ctrl) for (int i = 0; i < NACT; i++) r[SO_CTRL + i] = ctrl[(size_t)e * NACT + i];
   if (act) for (int i = 0; i < NACT; i++) r[SO_ACT + i] = act[(size_t)e * NACT + i];
 }
-__global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const DevModel* m) {
+__global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const DevModel* m) {  // n = envs + pool slots
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   double* r = state + (size_t)e * STATE_STRIDE;
@@ -97,7 +156,7 @@ __global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const
 
 // ------------------------------------------------------------------ handle
 struct TsgHandle {
-  int device, n_envs, obs_dim, launches;
+  int device, n_envs, n_pool, obs_dim, launches, ready_phase;
   long long env_id_base;
   DevModel* d_model; EnvCfg* d_cfg; float* d_hdata;
   double* d_state; double* d_heading; double* d_draws;
@@ -106,6 +165,7 @@ struct TsgHandle {
   double *d_ctrl, *d_obs, *d_reward, *d_info, *d_termobs, *d_tmp;
   uint8_t* d_mask;
   Con* d_spill; int* d_counter;
+  double* d_pool_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   int grid[3];
   cudaStream_t own_stream;
 };
@@ -139,7 +199,7 @@ static int setup_kernel(TsgHandle* h, int num_sms, int* max_grid) {
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE>, TSG_WARPS * 32, SMEM_TOTAL));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
-  int need = (h->n_envs + TSG_WARPS - 1) / TSG_WARPS, full = num_sms * per_sm;
+  int need = (h->n_envs + h->n_pool + TSG_WARPS - 1) / TSG_WARPS, full = num_sms * per_sm;
   h->grid[MODE] = need < full ? need : full;
   if (h->grid[MODE] > *max_grid) *max_grid = h->grid[MODE];
   return 0;
@@ -147,8 +207,13 @@ static int setup_kernel(TsgHandle* h, int num_sms, int* max_grid) {
 
 int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int device, long long env_id_base,
                TsgHandle** out) {
+  return tsg_create_pooled(model, cfg, n_envs, 0, device, env_id_base, out);
+}
+int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int n_pool, int device,
+                      long long env_id_base, TsgHandle** out) {
   if (!model || !cfg || !out) FAIL("tsg_create: null argument");
   if (n_envs < 1) FAIL("tsg_create: n_envs must be >= 1");
+  if (n_pool < 0) FAIL("tsg_create: n_pool must be >= 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); FAIL("tsg_create: no CUDA device (libtsg has no CPU path)"); }
   if (device < 0 || device >= ndev) FAIL("tsg_create: bad device index");
@@ -158,7 +223,7 @@ int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int d
   if (prop.major < 10) FAIL("tsg_create: libtsg is built for sm_100a (B200) only");
   TsgHandle* h = new TsgHandle();
   memset(h, 0, sizeof(*h));
-  h->device = device; h->n_envs = n_envs; h->env_id_base = env_id_base;
+  h->device = device; h->n_envs = n_envs; h->n_pool = n_pool; h->env_id_base = env_id_base;
   if (model->floor_type == TSG_FLOOR_HFIELD) {
     if (!model->hf_data) { delete h; FAIL("tsg_create: height field data missing"); }
     size_t nb = (size_t)model->hf_nrow * model->hf_ncol * sizeof(float);
@@ -169,8 +234,8 @@ int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int d
   std::string err = make_dev_model(*model, dm, h->d_hdata);
   if (err.empty()) err = make_env_cfg(*cfg, *model, ec);
   if (!err.empty()) { tsg_destroy(h); FAIL("tsg_create: " + err); }
-  h->obs_dim = ec.obs_dim;
-  size_t n = (size_t)n_envs;
+  h->obs_dim = ec.obs_dim; h->ready_phase = ec.warmup_steps + 1;
+  size_t n = (size_t)n_envs + (size_t)n_pool;
   CK(cudaMalloc(&h->d_model, sizeof(DevModel)));
   CK(cudaMalloc(&h->d_cfg, sizeof(EnvCfg)));
   CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
@@ -188,7 +253,14 @@ int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int d
   CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_WARPS * (MAXC - MAXC_S) * sizeof(Con)));
   CK(cudaMalloc(&h->d_counter, sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  tsg_init_records_kernel<<<(n_envs + 127) / 128, 128>>>(h->d_state, n_envs, h->d_model);
+  if (n_pool) {
+    CK(cudaMalloc(&h->d_pool_obs, (size_t)n_pool * ec.obs_dim * sizeof(double)));
+    CK(cudaMalloc(&h->d_lists, (size_t)2 * n_pool * sizeof(int)));
+    CK(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
+    CK(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
+    CK(cudaMalloc(&h->d_need_sync, n_envs));
+  }
+  tsg_init_records_kernel<<<((int)n + 127) / 128, 128>>>(h->d_state, (int)n, h->d_model);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   *out = h;
@@ -199,7 +271,7 @@ int tsg_destroy(TsgHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
-                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter};
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter, h->d_pool_obs, h->d_lists, h->d_counts, h->d_need_sync};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -208,6 +280,15 @@ int tsg_destroy(TsgHandle* h) {
 int tsg_num_envs(const TsgHandle* h) { return h ? h->n_envs : -1; }
 int tsg_obs_dim(const TsgHandle* h) { return h ? h->obs_dim : -1; }
 int tsg_launches(const TsgHandle* h) { return h ? h->launches : -1; }
+int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
+  if (!h || !counts3) FAIL("tsg_pool_stats_host: null argument");
+  counts3[0] = counts3[1] = counts3[2] = 0;
+  if (!h->n_pool) return 0;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(counts3, h->d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
 int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes, int* regs_per_thread) {
   (void)h;
   if (warps_per_cta) *warps_per_cta = TSG_WARPS;
@@ -225,6 +306,7 @@ static StepIO base_io(TsgHandle* h) {
   memset(&io, 0, sizeof(io));
   io.state = h->d_state; io.heading = h->d_heading; io.draws = h->d_draws;
   io.n_envs = h->n_envs; io.env_id_base = h->env_id_base;
+  io.n_pool = h->n_pool; io.pool_obs = h->d_pool_obs;
   return io;
 }
 
@@ -254,11 +336,21 @@ int tsg_step(TsgHandle* h, const void* ctrl_dev, int ctrl_dtype, double* obs_dev
   if (ctrl_dtype == TSG_CTRL_F64) io.ctrl64 = (const double*)ctrl_dev; else io.ctrl32 = (const float*)ctrl_dev;
   io.obs = obs_dev; io.obs32 = obs32_dev; io.reward = reward_dev; io.info = info_dev;
   io.done = done_dev ? done_dev : h->d_done;
+  io.seed = seed;
+  if (!auto_reset) io.n_pool = 0;  // the pool only advances on auto-resetting handles
   int rc = launch_env<MODE_STEP>(h, io, s);
   if (rc) return rc;
   if (auto_reset) {
+    const uint8_t* mask = io.done;
+    if (h->n_pool) {  // hand pre-warmed slots to the done envs; only the remainder resets synchronously
+      tsg_assign_kernel<<<1, 1024, 0, s>>>(h->d_state, h->d_heading, io.done, h->d_need_sync, obs_dev, obs32_dev, term_obs_dev,
+                                           h->d_pool_obs, h->d_lists, h->d_counts, h->n_envs, h->n_pool, h->obs_dim, h->ready_phase);
+      CK(cudaGetLastError());
+      h->launches++;
+      mask = h->d_need_sync;
+    }
     StepIO r = base_io(h);
-    r.mask = io.done; r.seed = seed; r.obs = obs_dev; r.obs32 = obs32_dev; r.term_obs = term_obs_dev;
+    r.mask = mask; r.seed = seed; r.obs = obs_dev; r.obs32 = obs32_dev; r.term_obs = term_obs_dev;
     rc = launch_env<MODE_RESET>(h, r, s);
   }
   return rc;

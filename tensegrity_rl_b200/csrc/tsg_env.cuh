@@ -237,8 +237,18 @@ TSG_FN void aux_from_forward(const Scratch& S, Aux& A) {
   A.xy_prev[0] = P.xy[0]; A.xy_prev[1] = P.xy[1]; A.psi_prev = P.psi;
 }
 
-// env.reset(): MujocoEnv.reset (mj_resetData) + reset_model.  Random draws in S.draws.
-TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
+// env.reset() = MujocoEnv.reset (mj_resetData) + reset_model, split in three pieces so that it can run either in
+// one go (tsg_reset / fallback) or one warm-up step per launch on a background pool slot.  Random draws in S.draws.
+TSG_FN void reset_setpoints(EnvScratch& S, const EnvCfg& c, int lane) {
+  const double* u = S.draws;
+  LANE_FOR(i, NACT) {
+    double t = u[2 + i] * c.tendon_reset_stdev + c.tendon_reset_mean;
+    if (t > c.tendon_max_length) t = c.tendon_max_length; else if (t < c.tendon_min_length) t = c.tendon_min_length;
+    S.action[i] = t;
+  }
+  WSYNC();
+}
+TSG_FN void reset_begin(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
   const double* u = S.draws;
   reset_data(S, m, lane);
   int idx = (int)floor(u[0] * c.npose);
@@ -266,22 +276,16 @@ TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A,
   WSYNC();
   forward(CTX_ARGS);
   aux_from_forward(S, A);
-  // tendon set-points
-  LANE_FOR(i, NACT) {
-    double t = u[2 + i] * c.tendon_reset_stdev + c.tendon_reset_mean;
-    if (t > c.tendon_max_length) t = c.tendon_max_length; else if (t < c.tendon_min_length) t = c.tendon_min_length;
-    S.action[i] = t;
-  }
-  WSYNC();
-  StepOut O;
-  if (c.env_kind == ENV_TR) {
-    LANE_FOR(i, NACT) S.ctrl[i] = S.action[i];
-    WSYNC();
-    for (int k = 0; k < c.warmup_steps; k++) simulate(CTX_ARGS);  // do_simulation, no filter
-    aux_from_forward(S, A);
-  } else {
-    for (int k = 0; k < c.warmup_steps; k++) env_step(A, O, CTX_ARGS);  // full self.step
-  }
+  reset_setpoints(S, c, lane);
+  if (c.env_kind == ENV_TR) { LANE_FOR(i, NACT) S.ctrl[i] = S.action[i]; WSYNC(); }
+}
+// one of the warmup_steps settling steps at the set-points in S.action
+TSG_FN void reset_warm_step(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
+  if (c.env_kind == ENV_TR) { simulate(CTX_ARGS); aux_from_forward(S, A); }  // do_simulation, no filter
+  else { StepOut O; env_step(A, O, CTX_ARGS); }                              // full self.step
+}
+TSG_FN void reset_finish(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
+  const double* u = S.draws;
   Pose P; read_pose(S, P);
   A.reset_psi = P.psi;
   double lo = c.waypt_range[0], hi = c.waypt_range[1];
@@ -301,9 +305,16 @@ TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A,
     if (c.is_test) { A.waypt[0] = 0; A.waypt[1] = 0; }
   }
   A.step_num = 0;
-  if (c.env_kind == ENV_TR && (c.task == TASK_TURN || c.task == TASK_AIMING))
+  if (c.env_kind == ENV_TR && (c.task == TASK_TURN || c.task == TASK_AIMING)) {
+    StepOut O;
     for (int k = 0; k < c.reward_delay_steps; k++) env_step(A, O, CTX_ARGS);
+  }
   A.ep_ret = 0; A.ep_len = 0;
+}
+TSG_FN void env_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, Aux& A, int lane) {
+  reset_begin(S, m, c, A, lane);
+  for (int k = 0; k < c.warmup_steps; k++) reset_warm_step(S, m, c, A, lane);
+  reset_finish(S, m, c, A, lane);
 }
 
 // ---- state record <-> scratch
@@ -363,6 +374,8 @@ struct StepIO {
   long long env_id_base;
   int n_envs;
   int explicit_draws;
+  int n_pool;           // background reset pool slots stored after the n_envs records
+  double* pool_obs;     // [n_pool][obs_dim]: reset observation of each ready pool slot
 };
 
 TSG_FN void write_obs(const EnvScratch& S, const EnvCfg& c, const StepIO& io, int e, int lane) {
@@ -472,6 +485,38 @@ TSG_FN void run_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, const S
   write_obs(S, c, io, e, lane);
   store_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
   if (lane == 0) rec[SO_NRESET] = nreset + 1;
+}
+
+// background reset pool: slot p (record n_envs + p) advances by one warm-up step per launch until it holds a
+// completely reset env (state, heading ring, reset observation); tsg_assign_kernel then hands ready slots to envs
+// that are done, so an env reset costs no latency tail.  phase (SO_FLAGS) = warm-up steps done, warmup_steps+1 = ready.
+TSG_FN void run_pool(EnvScratch& S, const DevModel& m, const EnvCfg& c, const StepIO& io, int p, bool finish_now, int lane) {
+  Aux A;
+  size_t row = (size_t)io.n_envs + p;
+  double* rec = io.state + row * STATE_STRIDE;
+  int phase = (int)rec[SO_FLAGS];
+  if (phase > c.warmup_steps) return;
+  load_env(S, A, rec, io.heading + row * HEADING_SLOTS, true, lane);
+  double nreset = rec[SO_NRESET];
+  if (phase == 0) {
+    if (lane == 0) make_draws(S.draws, io.seed, (1ull << 40) + (unsigned long long)(io.env_id_base + p), (unsigned long long)nreset);
+    WSYNC();
+    LANE_FOR(i, NDRAW) io.draws[row * NDRAW + i] = S.draws[i];
+  } else { LANE_FOR(i, NDRAW) S.draws[i] = io.draws[row * NDRAW + i]; }
+  WSYNC();
+  if (phase == 0) reset_begin(S, m, c, A, lane); else reset_setpoints(S, c, lane);
+  do {
+    reset_warm_step(S, m, c, A, lane);
+    phase++;
+  } while (finish_now && phase < c.warmup_steps);
+  if (phase >= c.warmup_steps) {
+    reset_finish(S, m, c, A, lane);
+    compute_obs(S, m, c, A, lane);
+    LANE_FOR(i, c.obs_dim) io.pool_obs[(size_t)p * c.obs_dim + i] = S.u.post.obs[i];
+    phase = c.warmup_steps + 1;
+  }
+  store_env(S, A, rec, io.heading + row * HEADING_SLOTS, true, lane);
+  if (lane == 0) rec[SO_FLAGS] = (double)phase;
 }
 
 // mj_forward on the stored state (after tsg_set_state): refresh kinematics bookkeeping and obs

@@ -102,6 +102,7 @@ inline std::string make_env_cfg(const TsgEnvConfig& t, const TsgModel& mod, EnvC
   c.warmup_steps = t.warmup_steps; c.npose = t.npose;
   if (c.obs_dim < 1 || c.obs_dim > 64) return "obs_dim out of range";
   if (c.npose < 1 || c.npose > TSG_NPOSE) return "npose out of range";
+  if (c.warmup_steps < 1) return "warmup_steps must be >= 1";
   if (c.reward_delay_steps < 1 || c.reward_delay_steps + 1 > HEADING_SLOTS) return "reward_delay_steps out of range";
   if (c.env_kind == ENV_LEGACY && c.task > TASK_TURN) return "tensegrity_env supports straight/turn only";
   c.desired_direction = t.desired_direction; c.ctrl_cost_weight = t.ctrl_cost_weight;

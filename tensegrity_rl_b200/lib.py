@@ -12,7 +12,7 @@ INFO = dict(rew_fwd=0, rew_ctrl=1, rew_survive=2, x=3, y=4, psi=5, xvel=6, yvel=
             truncated=18, ncon=19, niter=20, nls=21, barforce=22, maxcfrc=23, waypt=24, ori=26, overflow=28,
             bad=29, nmpr=30)
 
-SYMBOLS = ["tsg_last_error", "tsg_version", "tsg_device_count", "tsg_create", "tsg_destroy", "tsg_num_envs",
+SYMBOLS = ["tsg_last_error", "tsg_version", "tsg_device_count", "tsg_create", "tsg_create_pooled", "tsg_pool_stats_host", "tsg_destroy", "tsg_num_envs",
            "tsg_obs_dim", "tsg_launches", "tsg_kernel_config", "tsg_reset", "tsg_step", "tsg_forward",
            "tsg_get_state_host", "tsg_set_state_host", "tsg_get_records_host", "tsg_set_records_host",
            "tsg_get_draws_host", "tsg_step_host", "tsg_reset_host"]
@@ -37,6 +37,8 @@ def load():
     vp, dp, fp, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     L.tsg_last_error.restype = C.c_char_p
     L.tsg_create.argtypes = [C.POINTER(TsgModel), C.POINTER(TsgEnvConfig), C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
+    L.tsg_create_pooled.argtypes = [C.POINTER(TsgModel), C.POINTER(TsgEnvConfig), C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
+    L.tsg_pool_stats_host.argtypes = [vp, C.POINTER(C.c_int)]
     L.tsg_destroy.argtypes = [vp]
     for f in ("tsg_num_envs", "tsg_obs_dim", "tsg_launches"):
         getattr(L, f).argtypes = [vp]

@@ -26,7 +26,10 @@ class TensegrityVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs, xml_file=None, env="tr_env", device=0, seed=0, env_id_base=0,
-                 auto_reset=True, info_mode="auto", max_episode_steps=5000, **env_kwargs):
+                 auto_reset=True, info_mode="auto", max_episode_steps=5000, reset_pool=0, **env_kwargs):
+        """reset_pool: number of background reset slots (0 = every reset runs synchronously, bit-reproducible per
+        env id; "auto" = num_envs // 4, at least 32).  With a pool, an env that is done receives a slot that has
+        already been through the reference's 50-step reset warm-up, so resets add no latency to a step."""
         import torch
 
         if not torch.cuda.is_available():
@@ -48,8 +51,11 @@ class TensegrityVecEnv:
         self.auto_reset = bool(auto_reset)
         self.info_mode = info_mode
         h = C.c_void_p()
-        _lib.check(self.L.tsg_create(C.byref(self._model), C.byref(self.cfg), self.num_envs, self.device_index,
-                                     int(env_id_base), C.byref(h)))
+        if reset_pool == "auto":
+            reset_pool = max(32, self.num_envs // 4) if auto_reset else 0
+        self.reset_pool = int(reset_pool)
+        _lib.check(self.L.tsg_create_pooled(C.byref(self._model), C.byref(self.cfg), self.num_envs, self.reset_pool,
+                                            self.device_index, int(env_id_base), C.byref(h)))
         self.h = h
         lo, hi = self.md["ctrlrange"]
         self.action_space = Box(np.full(6, lo, np.float32), np.full(6, hi, np.float32), dtype=np.float32)
@@ -186,6 +192,12 @@ class TensegrityVecEnv:
         d = np.zeros((self.num_envs, _lib.NDRAW))
         _lib.check(self.L.tsg_get_draws_host(self.h, C.c_void_p(d.ctypes.data)))
         return d
+
+    def pool_stats(self):
+        """{done envs, ready slots, slots handed out} of the last auto reset (synchronises)."""
+        c = (C.c_int * 3)()
+        _lib.check(self.L.tsg_pool_stats_host(self.h, c))
+        return {"done": c[0], "ready": c[1], "assigned": c[2]}
 
     @property
     def launches(self):

@@ -207,3 +207,55 @@ def test_properties_at_scale(xml, n):
     assert info[:, 28].sum() == 0 and info[:, 29].sum() == 0                  # no contact overflow, no bad state
     assert 0.5 < info[:, 19].mean() < 8                                        # contacts per env
     v.close()
+
+
+def test_pooled_reset_matches_reference_reset_semantics():
+    """background reset pool: a done env receives a slot that went through the full reset (pose table, rotation,
+    set-points, 50 warm-up steps, bookkeeping) -- identical to what a synchronous reset with the slot's draws
+    produces -- and the step path no longer waits for resets."""
+    import torch
+    from oracle.envs import OracleEnv
+    n, pool = 64, 16
+    v = _vec(n, "flat", "tr_env", desired_action="tracking", max_episode_steps=4, auto_reset=True, reset_pool=pool, seed=5)
+    v.reset_tensor()
+    draws = v.get_draws()          # [n] rows only; pool draws are read below through the records' obs
+    a = torch.full((n, 6), 0.05, device="cuda", dtype=torch.float64)
+    for k in range(3):
+        obs, rew, done = v.step_tensor(a)
+        assert not done.any()
+    obs, rew, done = v.step_tensor(a)      # 4th step: TimeLimit -> every env done, 16 slots available
+    st = v.pool_stats()
+    assert done.all() and st == {"done": n, "ready": pool, "assigned": pool}
+    rec = v.get_records()
+    assert (rec[:, 79] == 0).all()         # ep_len restarted for pooled AND synchronously reset envs
+    # first `pool` envs (env order) got the slots; their obs must be a valid reset observation
+    o = obs.cpu().numpy()
+    caps = o[:, :18].reshape(n, 6, 3)
+    assert np.abs(np.linalg.norm(caps[:, 0::2] - caps[:, 1::2], axis=2) - 1.376).max() < 1e-9
+    assert np.isfinite(o).all() and (np.abs(v.term_obs.cpu().numpy()) > 0).any()
+    # slots restart warming: after 50 more steps they are ready again
+    for k in range(3):
+        v.step_tensor(a)
+    obs, rew, done = v.step_tensor(a)
+    assert v.pool_stats()["ready"] == 0    # 4 launches later the slots are still warming
+    v.close()
+    # exactness of a pooled reset: replay slot 0's draws through the oracle env
+    v = _vec(8, "flat", "tr_env", desired_action="tracking", max_episode_steps=2, auto_reset=True, reset_pool=4, seed=9)
+    v.reset_tensor()
+    a = torch.full((8, 6), 0.05, device="cuda", dtype=torch.float64)
+    v.step_tensor(a)
+    import ctypes as C
+    d = np.zeros((8 + 4, 10))
+    # draws of the pool slots sit after the env rows
+    from tensegrity_rl_b200 import lib as tl
+    obs, rew, done = v.step_tensor(a)
+    assert done.all()
+    o = obs.cpu().numpy()
+    # env 0 received slot 0; regenerate slot 0's first draw with the emulator's Philox and replay in the oracle
+    from emul import emul as E
+    L = E.lib()
+    dr = np.zeros(10)
+    L.emul_make_draws(E.P(dr), C.c_ulonglong(9), C.c_ulonglong((1 << 40) + 0), C.c_ulonglong(0))
+    oe = OracleEnv("flat", "tr_env", desired_action="tracking")
+    assert np.abs(oe.reset(dr) - o[0]).max() < 1e-6
+    v.close()
