@@ -63,6 +63,7 @@ typedef struct TsgHandle TsgHandle;
 #define TSG_INFO_OVERFLOW 28
 #define TSG_INFO_BAD 29
 #define TSG_INFO_NMPR 30
+#define TSG_INFO_RESET_PSI 31 /* heading at the last reset (reward direction of `straight`) */
 
 const char *tsg_last_error(void);
 int tsg_version(void);

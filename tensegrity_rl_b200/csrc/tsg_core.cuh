@@ -69,7 +69,7 @@ enum StateOff {
 enum InfoOff {
   IO_REW_FWD = 0, IO_REW_CTRL, IO_REW_SURVIVE, IO_X, IO_Y, IO_PSI, IO_XVEL, IO_YVEL,
   IO_TEN = 8 /* 9 */, IO_TERMINATED = 17, IO_TRUNCATED, IO_NCON, IO_NITER, IO_NLS, IO_BARFORCE, IO_MAXCFRC,
-  IO_WAYPT = 24 /* 2 */, IO_ORI = 26 /* 2 */, IO_OVERFLOW = 28, IO_BAD = 29, IO_NMPR = 30
+  IO_WAYPT = 24 /* 2 */, IO_ORI = 26 /* 2 */, IO_OVERFLOW = 28, IO_BAD = 29, IO_NMPR = 30, IO_RESET_PSI = 31
 };
 
 struct DevModel {

@@ -426,6 +426,7 @@ TSG_FN void run_step(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
         case IO_OVERFLOW: v = S.overflow; break;
         case IO_BAD: v = S.bad; break;
         case IO_NMPR: v = S.nmpr_total; break;
+        case IO_RESET_PSI: v = A.reset_psi; break;
         default: if (i >= IO_TEN && i < IO_TEN + 9) v = S.tlen[i - IO_TEN];
       }
       I[i] = v;

@@ -10,7 +10,7 @@ STATE_STRIDE, INFO_DIM, NDRAW, HEADING_SLOTS = 96, 32, 10, 32
 CTRL_F64, CTRL_F32 = 0, 1
 INFO = dict(rew_fwd=0, rew_ctrl=1, rew_survive=2, x=3, y=4, psi=5, xvel=6, yvel=7, ten=8, terminated=17,
             truncated=18, ncon=19, niter=20, nls=21, barforce=22, maxcfrc=23, waypt=24, ori=26, overflow=28,
-            bad=29, nmpr=30)
+            bad=29, nmpr=30, reset_psi=31)
 
 SYMBOLS = ["tsg_last_error", "tsg_version", "tsg_device_count", "tsg_create", "tsg_create_pooled", "tsg_pool_stats_host", "tsg_destroy", "tsg_num_envs",
            "tsg_obs_dim", "tsg_launches", "tsg_kernel_config", "tsg_reset", "tsg_step", "tsg_forward",

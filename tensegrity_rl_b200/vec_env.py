@@ -183,6 +183,9 @@ class TensegrityVecEnv:
         _lib.check(self.L.tsg_get_records_host(self.h, C.c_void_p(rec.ctypes.data)))
         return rec
 
+    def get_records_t(self):
+        return self.torch.as_tensor(self.get_records(), device=self.device)
+
     def set_records(self, rec):
         rec = np.ascontiguousarray(rec, np.float64)
         assert rec.shape == (self.num_envs, _lib.STATE_STRIDE)

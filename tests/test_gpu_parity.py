@@ -259,3 +259,41 @@ def test_pooled_reset_matches_reference_reset_semantics():
     oe = OracleEnv("flat", "tr_env", desired_action="tracking")
     assert np.abs(oe.reset(dr) - o[0]).max() < 1e-6
     v.close()
+
+
+def test_pretrained_policy_rollouts_distribution_level():
+    """BASELINE configs 3/4 in small: pretrained SAC actors drive the batched envs on the device; forward
+    displacement / yaw statistics agree with the same policy run through the oracle env at distribution level
+    (the dynamics are chaotic and the policy stochastic, so only moments are compared)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_rollouts as R
+    steps = 150
+    g = R.gpu_rollout("forward_flat", 2048, steps, deterministic=False)
+    o = R.oracle_rollout("forward_flat", 12, steps, deterministic=False)
+    print("gpu", {k: round(g[k], 4) for k in ("episodes", "disp_mean", "disp_std", "yaw_mean", "yaw_std", "return_mean", "length_mean")})
+    print("oracle", {k: round(o[k], 4) for k in ("episodes", "disp_mean", "disp_std", "yaw_mean", "yaw_std", "return_mean", "length_mean")})
+    assert g["overflow"] == 0 and g["bad"] == 0 and g["env_steps"] == 2048 * steps
+    # the policy was trained on another bar geometry / actuator law (DESIGN.md), so only consistency is asserted
+    se = max(g["disp_std"], o["disp_std"], 1e-3) / np.sqrt(max(o["episodes"], 1))
+    assert abs(g["disp_mean"] - o["disp_mean"]) < 5 * se + 0.02
+    sey = max(g["yaw_std"], o["yaw_std"], 1e-3) / np.sqrt(max(o["episodes"], 1))
+    assert abs(g["yaw_mean"] - o["yaw_mean"]) < 5 * sey + 0.02
+
+
+def test_test3_waypoint_selector_runs_batched():
+    import torch
+    from tensegrity_rl_b200 import SacActor
+    from tensegrity_rl_b200.rollout import WaypointController
+    n = 256
+    v = _vec(n, "flat", "tr_env", desired_action="aiming", is_test=True, auto_reset=False, terminate_when_unhealthy=False)
+    obs = v.reset_tensor()
+    assert torch.allclose(obs[:, 45:47], -torch.stack([v.get_records_t()[:, 69], v.get_records_t()[:, 70]], 1), atol=0.2)
+    ctl = WaypointController(v, SacActor("traj_track"), SacActor("traj_ccw"), SacActor("traj_cw"))
+    for k in range(30):
+        a = ctl.action(v.obs)
+        assert a.shape == (n, 6) and torch.isfinite(a).all()
+        v.step_tensor(a, auto_reset=False)
+        ctl.after_step(v.info)
+    assert torch.isfinite(v.obs).all() and (ctl.del_yaw.abs() <= np.pi + 1e-9).all()
+    v.close()
