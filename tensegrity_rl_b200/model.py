@@ -317,6 +317,13 @@ def load_model(xml_file=None):
     if os.path.isfile(xml_file) and xml_file.endswith(".json"):
         return load_model_json(xml_file)
     key = os.path.basename(xml_file)
+    if key == "legacy_flat":
+        # DERIVED variant (not a reference file): bars, sites, tendons and filter actuators of the uneven-ground
+        # XML on a flat plane at z = 0.  The SB3 checkpoints' `_last_obs` fit this bar geometry exactly and the
+        # pretrained policies reproduce the reference's training statistics on it (tests/test_gpu_parity.py).
+        md = dict(load_model("uneven"))
+        md.update(floor_type=FLOOR_PLANE, floor_pos=[0.0, 0.0, 0.0], hfield=None, source="derived: uneven XML bars on a plane")
+        return md
     name = {"flat": "model_flat.json", "uneven": "model_uneven.json"}.get(key, _ASSET_BY_XML.get(key))
     if name is None:
         raise FileNotFoundError(f"model file not found: {xml_file}")

@@ -297,3 +297,34 @@ def test_test3_waypoint_selector_runs_batched():
         ctl.after_step(v.info)
     assert torch.isfinite(v.obs).all() and (ctl.del_yaw.abs() <= np.pi + 1e-9).all()
     v.close()
+
+
+def test_pretrained_policies_reproduce_reference_training_statistics():
+    """Distribution-level pin against numbers produced by the REFERENCE'S OWN MuJoCo runs: every SB3 checkpoint
+    stores the last 100 training episodes (return, length).  On the model the checkpoints were trained on
+    (bar geometry pinned by tests/test_golden_last_obs.py; flat floor) the pretrained policies must reproduce the
+    per-step return, i.e. the gait speed / yaw rate, they had at training time:
+        forward  1537 / 3971 = 0.387 per step  (0.29 m/s + 0.1 healthy - ctrl cost)
+        backward 1643 / 3613 = 0.455 per step
+        yaw CCW   207 / 2605 = 0.080 rad/s ;  yaw CW 178 / 2089 = 0.085 rad/s
+    A gait learned by RL is sensitive to contact, friction, actuator and integrator details, so this checks the
+    whole dynamics restatement, not just kinematics."""
+    import json, os
+    from tensegrity_rl_b200 import SacActor
+    from tensegrity_rl_b200.rollout import rollout
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "last_obs.json")))
+    cases = [("forward", dict(desired_action="straight", desired_direction=1), "return"),
+             ("backward", dict(desired_action="straight", desired_direction=-1), "return"),
+             ("yaw_CCW", dict(desired_action="turn", desired_direction=1, terminate_when_unhealthy=False), "return"),
+             ("yaw_CW", dict(desired_action="turn", desired_direction=-1, terminate_when_unhealthy=False), "return")]
+    for pol, kw, _ in cases:
+        ref = G[pol]["ep_return_mean"] / G[pol]["ep_len_mean"]
+        v = _vec(1024, "legacy_flat", "tensegrity_env", auto_reset=True, reset_pool=256, **kw)
+        v.reset_tensor()
+        s = rollout(v, SacActor(pol), 500)
+        got = s["return_sum"] / s["length_sum"]
+        speed = s["disp_sum"] / (s["length_sum"] * v.dt)
+        print(pol, "return/step ours %.3f reference %.3f | forward speed %.3f m/s yaw rate %.3f rad/s"
+              % (got, ref, speed, s["yaw_sum"] / (s["length_sum"] * v.dt)))
+        assert abs(got - ref) < 0.2 * abs(ref) + 0.01, (pol, got, ref)
+        v.close()
