@@ -13,17 +13,31 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
-def is_stale():
-    return not os.path.isfile(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS)
+STAMP = SO + ".stamp"   # hash of sources + flags the existing .so was built from (travels with it to the GPU box)
+
+
+def _digest(extra=()):
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + list(extra)).encode())
+    for d in DEPS:
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
+def is_stale(extra=()):
+    if not os.path.isfile(SO) or not os.path.isfile(STAMP):
+        return True
+    return open(STAMP).read().strip() != _digest(extra)
 
 
 def build(force=False, verbose=False, extra=()):
-    if not force and not is_stale():
+    if not force and not is_stale(extra):
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
     print("[tsg build]", " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+    open(STAMP, "w").write(_digest(extra))
     return SO
 
 

@@ -1,6 +1,7 @@
 // tsg_api.cu -- kernels and the C ABI (include/tsg.h) of libtsg.so.  sm_100a only.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -10,11 +11,13 @@
 
 using namespace tsg;
 
+// Production configuration (profiles/): full warps per env, 8 warps per CTA, 2 CTAs per SM (128 registers), the
+// warps of a CTA aligned at substep / Newton-iteration granularity (TSG_ALIGN, default set in tsg_core.cuh).
 #ifndef TSG_MIN_CTAS
-#define TSG_MIN_CTAS 4  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
+#define TSG_MIN_CTAS 2  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
 #endif
 #ifndef TSG_WARPS
-#define TSG_WARPS 4  // warps (= envs in flight) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
+#define TSG_WARPS 8  // warps (= envs in flight) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
 #endif
 
 static_assert(STATE_STRIDE == TSG_STATE_STRIDE && INFO_DIM == TSG_INFO_DIM && NDRAW == TSG_NDRAW, "ABI constants");
@@ -23,7 +26,8 @@ static_assert(HEADING_SLOTS == TSG_HEADING_SLOTS, "heading slots");
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 
-constexpr size_t SMEM_TOTAL = SMEM_MODEL + SMEM_CFG + TSG_WARPS * SMEM_SCRATCH;
+constexpr int TSG_VWARPS = TSG_WARPS * (32 / TSG_VW);  // virtual warps (= envs in flight) per CTA
+constexpr size_t SMEM_TOTAL = SMEM_MODEL + SMEM_CFG + TSG_VWARPS * SMEM_SCRATCH;
 
 // One warp per env, persistent CTAs: the grid is sized to fill the machine once (SMs x resident CTAs) and every
 // warp pulls env indices from a global counter until the batch is done, so envs of different cost (contact
@@ -47,23 +51,57 @@ __global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(c
   __syncthreads();
   const DevModel& m = *reinterpret_cast<const DevModel*>(smem);
   const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(smem + SMEM_MODEL);
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int warp = threadIdx.x / TSG_VW, lane = threadIdx.x % TSG_VW;  // virtual warp / lane
   EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
-  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * TSG_WARPS + warp) * (MAXC - MAXC_S);
-  __syncwarp();
+  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * TSG_VWARPS + warp) * (MAXC - MAXC_S);
+  WSYNC();
   // items: the n_envs envs, then (STEP: every launch, RESET of all envs: prewarm) the background reset pool slots
   int n_items = io.n_envs + ((MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? io.n_pool : 0);
+  int first = 0;  // first item of the unaligned loop below
+#if TSG_ALIGNED
+  // aligned work loop over the envs: the envs of one alignment scope (physical warp / CTA) are fetched together and
+  // walk through the step in phase; a (virtual) warp without an env at the tail runs the idle barrier protocol.
+  // Pool slots (mostly idle) are left to the unaligned loop.
+  if (MODE == MODE_STEP) {
+#ifdef TSG_ALIGN_WARP
+    constexpr int GROUP = 32 / TSG_VW;
+    for (;;) {
+      int base = 0;
+      if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, GROUP);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= io.n_envs) break;
+      int e = base + (threadIdx.x & 31) / TSG_VW;
+#else
+    __shared__ int s_base;
+    for (;;) {
+      if (threadIdx.x == 0) s_base = atomicAdd(counter, TSG_VWARPS);
+      __syncthreads();
+      int e = s_base + warp;
+      __syncthreads();
+      if (e - warp >= io.n_envs) break;
+#endif
+      if (lane == 0) S.align = 1;
+      WSYNC();
+      if (e < io.n_envs) run_step(S, m, c, io, e, lane);
+      else for (int s = 0; s < c.frame_skip; s++) aligned_idle_substep();
+    }
+    first = io.n_envs;
+    counter += 1;  // the pool items use the second counter
+  }
+#endif
+  if (lane == 0) S.align = 0;
+  WSYNC();
   for (;;) {
     int e = 0;
-    if (lane == 0) e = atomicAdd(counter, 1);
-    e = __shfl_sync(0xffffffffu, e, 0);
+    if (lane == 0) e = first + atomicAdd(counter, 1);
+    e = __shfl_sync(TSG_VMASK(), e, 0, TSG_VW);
     if (e >= n_items) break;
-    if (e >= io.n_envs) { run_pool(S, m, c, io, e - io.n_envs, MODE == MODE_RESET, lane); __syncwarp(); continue; }
+    if (e >= io.n_envs) { run_pool(S, m, c, io, e - io.n_envs, MODE == MODE_RESET, lane); WSYNC(); continue; }
     if (MODE == MODE_RESET && io.mask && !io.mask[e]) continue;
     if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
     else if (MODE == MODE_RESET) run_reset(S, m, c, io, e, lane);
     else run_forward(S, m, c, io, e, lane);
-    __syncwarp();
+    WSYNC();
   }
 }
 
@@ -185,21 +223,27 @@ int tsg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
   } while (0)
 #define FAIL(msg) do { g_err = (msg); return -1; } while (0)
 
+// TSG_EXTRA_SMEM (bytes, env var; measurement aid): pads the dynamic shared memory per CTA to lower the occupancy
+static size_t extra_smem() {
+  static long v = -1;
+  if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
+  return (size_t)v;
+}
 template <int MODE>
 static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
-  CK(cudaMemsetAsync(h->d_counter, 0, sizeof(int), s));
-  tsg_env_kernel<MODE><<<h->grid[MODE], TSG_WARPS * 32, SMEM_TOTAL, s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
+  CK(cudaMemsetAsync(h->d_counter, 0, 2 * sizeof(int), s));
+  tsg_env_kernel<MODE><<<h->grid[MODE], TSG_WARPS * 32, SMEM_TOTAL + extra_smem(), s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
 }
 template <int MODE>
 static int setup_kernel(TsgHandle* h, int num_sms, int* max_grid) {
-  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_TOTAL + extra_smem())));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE>, TSG_WARPS * 32, SMEM_TOTAL));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE>, TSG_WARPS * 32, SMEM_TOTAL + extra_smem()));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
-  int need = (h->n_envs + h->n_pool + TSG_WARPS - 1) / TSG_WARPS, full = num_sms * per_sm;
+  int need = (h->n_envs + h->n_pool + TSG_VWARPS - 1) / TSG_VWARPS, full = num_sms * per_sm;
   h->grid[MODE] = need < full ? need : full;
   if (h->grid[MODE] > *max_grid) *max_grid = h->grid[MODE];
   return 0;
@@ -250,8 +294,8 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
   int max_grid = 0;
   if (setup_kernel<MODE_STEP>(h, prop.multiProcessorCount, &max_grid) || setup_kernel<MODE_RESET>(h, prop.multiProcessorCount, &max_grid) ||
       setup_kernel<MODE_FORWARD>(h, prop.multiProcessorCount, &max_grid)) { tsg_destroy(h); return -2; }
-  CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_WARPS * (MAXC - MAXC_S) * sizeof(Con)));
-  CK(cudaMalloc(&h->d_counter, sizeof(int)));
+  CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_VWARPS * (MAXC - MAXC_S) * sizeof(Con)));
+  CK(cudaMalloc(&h->d_counter, 2 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   if (n_pool) {
     CK(cudaMalloc(&h->d_pool_obs, (size_t)n_pool * ec.obs_dim * sizeof(double)));
@@ -291,7 +335,7 @@ int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
 }
 int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes, int* regs_per_thread) {
   (void)h;
-  if (warps_per_cta) *warps_per_cta = TSG_WARPS;
+  if (warps_per_cta) *warps_per_cta = TSG_WARPS * 100 + TSG_VW;  // physical warps per CTA * 100 + lanes per env
   if (smem_bytes) *smem_bytes = (int)SMEM_TOTAL;
   if (regs_per_thread) {
     cudaFuncAttributes a;

@@ -25,9 +25,20 @@
 #define TSG_FN __device__ __forceinline__
 #define TSG_FN_NOINLINE __device__ __noinline__
 #define TSG_UNROLL1 _Pragma("unroll 1")
-#define LANE_FOR(i, n) for (int i = lane; i < (n); i += 32)
-#define LANE_FOR_ALL(i, n) for (int i##_b = 0, i = lane; i##_b < (n); i##_b += 32, i += 32)
-#define WSYNC() __syncwarp()
+// Virtual warp: TSG_VW lanes (32, 16 or 8) cooperate on one env, so 32 / TSG_VW envs share every instruction a
+// physical warp fetches while their control flow coincides (the kernel is instruction-fetch bound); where it does
+// not, SIMT divergence serialises them.  `lane` is the lane inside the virtual warp everywhere below.
+#ifndef TSG_VW
+#define TSG_VW 32
+#endif
+// default alignment scope: the CTA (see align_any below); -DTSG_NO_ALIGN builds the free-running variant
+#if !defined(TSG_ALIGN) && !defined(TSG_ALIGN_WARP) && !defined(TSG_NO_ALIGN)
+#define TSG_ALIGN 1
+#endif
+#define TSG_VMASK() ((TSG_VW == 32) ? 0xffffffffu : ((((1u << (TSG_VW & 31)) - 1u)) << ((threadIdx.x & 31) / TSG_VW * TSG_VW)))
+#define LANE_FOR(i, n) for (int i = lane; i < (n); i += TSG_VW)
+#define LANE_FOR_ALL(i, n) for (int i##_b = 0, i = lane; i##_b < (n); i##_b += TSG_VW, i += TSG_VW)
+#define WSYNC() __syncwarp(TSG_VMASK())
 #else
 #define TSG_DEVICE 0
 #define TSG_FN static inline
@@ -159,6 +170,7 @@ struct Scratch {
   int order[MAXC];
   int nact, nslot, overflow, bad;
   int niter_total, nls_total, nmpr_total, ls_evals;
+  int align, pad2;
 };
 
 struct EnvScratch : Scratch {
@@ -178,7 +190,7 @@ constexpr size_t SMEM_SCRATCH = align16(sizeof(EnvScratch));
 #define CTX_ARGS lane
 #define CTX_BIND                                                                                         \
   extern __shared__ __align__(16) unsigned char tsg_smem[];                                              \
-  EnvScratch& S = *reinterpret_cast<EnvScratch*>(tsg_smem + SMEM_MODEL + SMEM_CFG + (threadIdx.x >> 5) * SMEM_SCRATCH); \
+  EnvScratch& S = *reinterpret_cast<EnvScratch*>(tsg_smem + SMEM_MODEL + SMEM_CFG + (threadIdx.x / TSG_VW) * SMEM_SCRATCH); \
   const DevModel& m = *reinterpret_cast<const DevModel*>(tsg_smem);                                      \
   const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tsg_smem + SMEM_MODEL);                             \
   (void)c; (void)m;
@@ -270,13 +282,14 @@ TSG_FN double clampd(double x, double lo, double hi) { return fmin(hi, fmax(lo, 
 TSG_FN int scan_slot(int v, int& total, int lane) {
 #if TSG_DEVICE
   int incl = v;
+  const unsigned vm = TSG_VMASK();
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, o);
+  for (int o = 1; o < TSG_VW; o <<= 1) {
+    int t = __shfl_up_sync(vm, incl, o, TSG_VW);
     if (lane >= o) incl += t;
   }
   int slot = total + incl - v;
-  total += __shfl_sync(0xffffffffu, incl, 31);
+  total += __shfl_sync(vm, incl, TSG_VW - 1, TSG_VW);
   return slot;
 #else
   (void)lane;
@@ -1241,51 +1254,90 @@ TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   return 0;
 }
 
+// Alignment scope: the envs that share a physical warp (TSG_ALIGN_WARP, with TSG_VW < 32) or the whole CTA
+// (TSG_ALIGN) walk through the same sequence of phases, idle where they have nothing to do, so that they share
+// fetched instructions.  cta_any = barrier + "is any env of the scope still active"; align_sync = plain barrier.
+#if TSG_DEVICE && defined(TSG_ALIGN_WARP)
+#define TSG_ALIGNED 1
+TSG_FN bool align_any(bool go) { return __any_sync(0xffffffffu, go) != 0; }
+TSG_FN void align_sync() { __syncwarp(0xffffffffu); }
+#elif TSG_DEVICE && defined(TSG_ALIGN)
+#define TSG_ALIGNED 1
+TSG_FN bool align_any(bool go) { return __syncthreads_or(go ? 1 : 0) != 0; }
+TSG_FN void align_sync() { __syncthreads(); }
+#else
+#define TSG_ALIGNED 0
+#endif
+TSG_FN bool cta_any(const Scratch& S, bool go) {
+#if TSG_ALIGNED
+  if (S.align) return align_any(go);
+#endif
+  return go;
+}
 // mj_fwdConstraint: warm-start choice + Newton iterations.  Leaves S.qacc, S.fcon, S.warm.
+// In aligned mode every warp of the CTA walks through the same sequence of phases (idle where it has nothing to
+// do), which keeps the instruction stream of the SM coherent: the kernel is instruction-fetch bound.
 TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int lane) {
-  if (S.nact == 0) {
+  bool active = S.nact > 0;
+  if (!active) {
     LANE_FOR(i, NV) { S.qacc[i] = S.asmooth[i]; S.warm[i] = S.asmooth[i]; S.fcon[i] = 0; }
     WSYNC();
-    return;
+    if (!S.align) return;
   }
-  // cost at qacc_smooth (Gauss term 0), then at the warm start
-  compute_jar(VEC_SMOOTH, CTX_ARGS);
-  double cost_sm = total_cost(VEC_SMOOTH, 0, CTX_ARGS);
-  compute_jar(VEC_WARM, CTX_ARGS);
-  double cost_ws = total_cost(VEC_WARM, 0, CTX_ARGS);
-  bool use_smooth = cost_ws > cost_sm;
-  LANE_FOR(i, NV) S.qacc[i] = use_smooth ? S.asmooth[i] : S.warm[i];
-  WSYNC();
-  if (use_smooth) compute_jar(VEC_QACC, CTX_ARGS);
-  double cost = total_cost(VEC_QACC, 1, CTX_ARGS);
-  newton_direction(CTX_ARGS);
+  double cost = 0;
+  cta_any(S, true);
+  if (active) {
+    // cost at qacc_smooth (Gauss term 0), then at the warm start
+    compute_jar(VEC_SMOOTH, CTX_ARGS);
+    double cost_sm = total_cost(VEC_SMOOTH, 0, CTX_ARGS);
+    compute_jar(VEC_WARM, CTX_ARGS);
+    double cost_ws = total_cost(VEC_WARM, 0, CTX_ARGS);
+    bool use_smooth = cost_ws > cost_sm;
+    LANE_FOR(i, NV) S.qacc[i] = use_smooth ? S.asmooth[i] : S.warm[i];
+    WSYNC();
+    if (use_smooth) compute_jar(VEC_QACC, CTX_ARGS);
+    cost = total_cost(VEC_QACC, 1, CTX_ARGS);
+  }
+  cta_any(S, true);
+  if (active) newton_direction(CTX_ARGS);
   double scale = tsg_div(1.0, m.meaninertia * NV);
   int iter = 0, nls = 0;
   TSG_UNROLL1
-  while (iter < m.iterations) {
-    double alpha = line_search(CTX_ARGS);
-    nls += S.ls_evals;
-    if (alpha == 0) break;
-    WSYNC();
-    LANE_FOR(i, NV + S.nact * 6) {
-      if (i < NV) S.qacc[i] += alpha * S.search[i];
-      else { int n = (i - NV) / 6, r = (i - NV) % 6; Con& k = con_at(S, S.order[n]); k.jar[r] += alpha * k.aref[r]; }
+  for (;;) {
+    bool go = active && iter < m.iterations;
+    if (!cta_any(S, go)) break;
+    double alpha = 0;
+    if (go) {
+      alpha = line_search(CTX_ARGS);
+      nls += S.ls_evals;
+      if (alpha == 0) active = false;
     }
-    WSYNC();
-    double oldcost = cost;
-    cost = total_cost(VEC_QACC, 1, CTX_ARGS);
-    newton_direction(CTX_ARGS);
-    double gn = 0;
-    TSG_UNROLL1
-    for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
-    double improvement = scale * (oldcost - cost), gradient = scale * tsg_sqrt(gn);
-    iter++;
-    if (improvement < m.tol || gradient < m.tol) break;
+    bool upd = go && active;
+    cta_any(S, true);
+    if (upd) {
+      WSYNC();
+      LANE_FOR(i, NV + S.nact * 6) {
+        if (i < NV) S.qacc[i] += alpha * S.search[i];
+        else { int n = (i - NV) / 6, r = (i - NV) % 6; Con& k = con_at(S, S.order[n]); k.jar[r] += alpha * k.aref[r]; }
+      }
+      WSYNC();
+      double oldcost = cost;
+      cost = total_cost(VEC_QACC, 1, CTX_ARGS);
+      newton_direction(CTX_ARGS);
+      double gn = 0;
+      TSG_UNROLL1
+      for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
+      double improvement = scale * (oldcost - cost), gradient = scale * tsg_sqrt(gn);
+      iter++;
+      if (improvement < m.tol || gradient < m.tol) active = false;
+    }
   }
-  WSYNC();
-  LANE_FOR(i, NV) S.warm[i] = S.qacc[i];
-  if (lane == 0) { S.niter_total += iter; S.nls_total += nls; }
-  WSYNC();
+  if (S.nact > 0) {
+    WSYNC();
+    LANE_FOR(i, NV) S.warm[i] = S.qacc[i];
+    if (lane == 0) { S.niter_total += iter; S.nls_total += nls; }
+    WSYNC();
+  }
 }
 
 // ------------------------------------------------------------------ implicitfast + advance
@@ -1363,6 +1415,7 @@ TSG_FN_NOINLINE void forward(CTX_PARAMS) {
   stage_position(S, m, lane);
   stage_tendon(S, m, lane);
   stage_smooth(S, m, lane);
+  cta_any(S, true);
   stage_constraint(S, m, lane);
   stage_solve(S, m, c, lane);
 }
@@ -1379,9 +1432,31 @@ TSG_FN_NOINLINE void substep(CTX_PARAMS) {
   bad = false;
   for (int i = 0; i < NV; i++) bad |= is_bad(S.qacc[i]);  // mj_checkAcc
   WSYNC();
-  if (bad) { if (lane == 0) S.bad |= 4; reset_data(S, m, lane); forward(CTX_ARGS); }
+  if (bad) {  // the repeated forward pass runs unaligned: its CTA barriers have no partners
+    int al = S.align;
+    if (lane == 0) { S.bad |= 4; S.align = 0; }
+    reset_data(S, m, lane); forward(CTX_ARGS);
+    if (lane == 0) S.align = al;
+    WSYNC();
+  }
   stage_integrate(S, m, lane);
 }
+
+#if TSG_ALIGNED
+// barrier protocol of one aligned substep for a (virtual) warp that has no env (tail of the batch): must mirror
+// simulate() -> forward() -> stage_solve() exactly
+// (the SAME barrier primitive as the working warps at every point: a plain and a reducing barrier must not meet)
+TSG_FN void aligned_idle_substep() {
+  align_sync();            // simulate: substep start
+  align_any(true);         // forward: before stage_constraint
+  align_any(true);         // stage_solve: before the warm-start costs
+  align_any(true);         // stage_solve: before the first Newton direction
+  for (;;) {
+    if (!align_any(false)) break;
+    align_any(true);
+  }
+}
+#endif
 
 // mj_rnePostConstraint: cfrc_ext rows [torque; force] for world + 3 bars, from the last forward pass
 TSG_FN void stage_cfrc(Scratch& S, const DevModel& m, int lane) {

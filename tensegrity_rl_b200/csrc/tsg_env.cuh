@@ -120,7 +120,12 @@ TSG_FN void compute_obs(EnvScratch& S, const DevModel& m, const EnvCfg& c, const
 // do_simulation(ctrl, frame_skip): ctrl already in S.ctrl
 TSG_FN_NOINLINE void simulate(CTX_PARAMS) {
   CTX_BIND
-  for (int s = 0; s < c.frame_skip; s++) substep(CTX_ARGS);
+  for (int s = 0; s < c.frame_skip; s++) {
+#if TSG_ALIGNED
+    if (S.align) align_sync();
+#endif
+    substep(CTX_ARGS);
+  }
   stage_cfrc(S, m, lane);
 }
 
@@ -505,9 +510,18 @@ TSG_FN void run_pool(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
     LANE_FOR(i, NDRAW) io.draws[row * NDRAW + i] = S.draws[i];
   } else { LANE_FOR(i, NDRAW) S.draws[i] = io.draws[row * NDRAW + i]; }
   WSYNC();
+  // only the single warm-up step of a launch follows the aligned barrier protocol (exactly one simulate());
+  // the begin / finish parts contain extra forward passes and steps and run unaligned
+  int aligned = S.align && !finish_now;
+  if (lane == 0) S.align = 0;
+  WSYNC();
   if (phase == 0) reset_begin(S, m, c, A, lane); else reset_setpoints(S, c, lane);
   do {
+    if (lane == 0) S.align = aligned;
+    WSYNC();
     reset_warm_step(S, m, c, A, lane);
+    if (lane == 0) S.align = 0;
+    WSYNC();
     phase++;
   } while (finish_now && phase < c.warmup_steps);
   if (phase >= c.warmup_steps) {
