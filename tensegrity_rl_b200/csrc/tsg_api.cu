@@ -11,10 +11,11 @@
 
 using namespace tsg;
 
-// Production configuration (profiles/): full warps per env, 8 warps per CTA, 2 CTAs per SM (128 registers), the
+// Production configuration (profiles/): full warps per env, 8 warps per CTA, 3 CTAs per SM (24 warps, <= 85 registers,
+// 3 contact slots per env in shared memory), the
 // warps of a CTA aligned at substep / Newton-iteration granularity (TSG_ALIGN, default set in tsg_core.cuh).
 #ifndef TSG_MIN_CTAS
-#define TSG_MIN_CTAS 2  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
+#define TSG_MIN_CTAS 3  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
 #endif
 #ifndef TSG_WARPS
 #define TSG_WARPS 8  // warps (= envs in flight) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)

@@ -56,7 +56,10 @@
 namespace tsg {
 
 constexpr int NBAR = 3, NGEOM = 15, NTEN = 9, NEND = 18, NACT = 6, NQ = 21, NV = 18;
-constexpr int MAXC_S = 6;       // contact slots per env in shared memory
+#ifndef TSG_MAXC_S
+#define TSG_MAXC_S 3  // measured: fewer resident slots -> more resident warps wins; the typical env has 2-3 contacts
+#endif
+constexpr int MAXC_S = TSG_MAXC_S;       // contact slots per env in shared memory
 constexpr int MAXC = 32;        // total contact slots per env (slots >= MAXC_S spill to a per-warp global area)
 constexpr int MAXCAND = 64;     // narrow-phase candidates per collision pass
 constexpr int NTRI = NV * (NV + 1) / 2;  // packed lower triangle of the Hessian
@@ -1072,8 +1075,9 @@ TSG_FN void Jcol(const Con& c, int side, int k, double* col) {
   }
 }
 
-// gradient, Hessian, Cholesky, search = -H^-1 grad.  Needs total_cost(.., full) done.
-TSG_FN_NOINLINE void newton_direction(CTX_PARAMS) {
+// gradient (+ qfrc_constraint), then -- unless `grad_only` -- Hessian, factorisation, search = -H^-1 grad.
+// Needs total_cost(.., full) done.  Returns |grad|^2.  The converged last iteration only needs the gradient.
+TSG_FN_NOINLINE double newton_direction(int grad_only, double oldcost, double cost, CTX_PARAMS) {
   CTX_BIND
   int nact = S.nact;
   // cone vectors b = sum_j su_j J_j  (item = contact, side, dof)
@@ -1104,6 +1108,13 @@ TSG_FN_NOINLINE void newton_direction(CTX_PARAMS) {
     S.grad[i] = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
   }
   WSYNC();
+  double gn = 0;
+  TSG_UNROLL1
+  for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
+  if (grad_only) {  // convergence test of mj_solPrimal: skip the factorisation nobody will use
+    double scale = tsg_div(1.0, m.meaninertia * NV);
+    if (scale * (oldcost - cost) < m.tol || scale * tsg_sqrt(gn) < m.tol) return -1.0;
+  }
   // Hessian, packed lower triangle (item = entry)
   LANE_FOR(e, NTRI) {
     int i = m.tri_i[e], j = m.tri_j[e];
@@ -1131,6 +1142,7 @@ TSG_FN_NOINLINE void newton_direction(CTX_PARAMS) {
   }
   WSYNC();
   factor_solve(S, lane);
+  return gn;
 }
 
 struct LsPnt { double alpha, cost, d0, d1; };
@@ -1299,8 +1311,7 @@ TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int l
     cost = total_cost(VEC_QACC, 1, CTX_ARGS);
   }
   cta_any(S, true);
-  if (active) newton_direction(CTX_ARGS);
-  double scale = tsg_div(1.0, m.meaninertia * NV);
+  if (active) newton_direction(0, 0.0, 0.0, CTX_ARGS);
   int iter = 0, nls = 0;
   TSG_UNROLL1
   for (;;) {
@@ -1313,7 +1324,9 @@ TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int l
       if (alpha == 0) active = false;
     }
     bool upd = go && active;
+#ifndef TSG_ONE_BARRIER
     cta_any(S, true);
+#endif
     if (upd) {
       WSYNC();
       LANE_FOR(i, NV + S.nact * 6) {
@@ -1323,13 +1336,8 @@ TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int l
       WSYNC();
       double oldcost = cost;
       cost = total_cost(VEC_QACC, 1, CTX_ARGS);
-      newton_direction(CTX_ARGS);
-      double gn = 0;
-      TSG_UNROLL1
-      for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
-      double improvement = scale * (oldcost - cost), gradient = scale * tsg_sqrt(gn);
       iter++;
-      if (improvement < m.tol || gradient < m.tol) active = false;
+      if (newton_direction(1, oldcost, cost, CTX_ARGS) < 0) active = false;   // converged
     }
   }
   if (S.nact > 0) {
@@ -1453,7 +1461,9 @@ TSG_FN void aligned_idle_substep() {
   align_any(true);         // stage_solve: before the first Newton direction
   for (;;) {
     if (!align_any(false)) break;
+#ifndef TSG_ONE_BARRIER
     align_any(true);
+#endif
   }
 }
 #endif
