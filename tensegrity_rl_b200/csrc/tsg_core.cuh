@@ -160,7 +160,7 @@ struct Scratch {
   double fsm[NV], asmooth[NV], fcon[NV];
   // solver vectors
   double qacc[NV], grad[NV], search[NV], rhs[NV], dinv[NV];
-  double qG[3], lsr[3], gauss;
+  double qG[3], lsr[3], gauss, cost;
   // time-multiplexed region: collision temporaries -> Hessian -> line-search sums -> post-solve data
   union {
     struct { int cand[MAXCAND]; int hf_cell[NGEOM][4]; double hf_zmin[NGEOM]; } col;
@@ -1013,11 +1013,13 @@ TSG_FN_NOINLINE double total_cost(int which, int full, CTX_PARAMS) {
   }
   WSYNC();
   S.gauss = g;
+  S.cost = s + g;
   return s + g;
 }
 
 // H = L D L^T of the packed Hessian in shared memory (lane i owns row i; no square roots; structurally zero
-// columns -- bars not coupled by a contact -- are skipped), then forward / diagonal / backward substitution
+// columns -- bars not coupled by a contact -- are skipped).  The right-hand side rides along as an extra column, so
+// the forward substitution costs no extra phases; columns keep their raw entries t_ik = L_ik d_k (scaled on use).
 TSG_FN void factor_solve(Scratch& S, int lane) {
   double* H = S.u.hes.H;
   LANE_FOR(i, NV) S.rhs[i] = S.grad[i];
@@ -1026,37 +1028,31 @@ TSG_FN void factor_solve(Scratch& S, int lane) {
   for (int k = 0; k < NV - 1; k++) {
     int kk = k * (k + 1) / 2;
     double dk = fmax(H[kk + k], MINVAL), inv = tsg_rcp(dk);
-    // column k still holds the raw entries t_ik = L_ik d_k during the update (read by every lane)
-    LANE_FOR(i, NV) if (i > k) {
-      double* Hi = H + i * (i + 1) / 2;
-      double t = Hi[k];
-      if (t != 0.0) {
-        double lik = t * inv;
-        TSG_UNROLL1
-        for (int j = k + 1; j < i; j++) Hi[j] -= lik * H[j * (j + 1) / 2 + k];
-        Hi[i] -= lik * t;
-      }
+    double yk = S.rhs[k];   // final: every earlier column has been eliminated
+    LANE_FOR(i, NV) {
+      if (i > k) {
+        double* Hi = H + i * (i + 1) / 2;
+        double t = Hi[k];
+        if (t != 0.0) {
+          double lik = t * inv;
+          TSG_UNROLL1
+          for (int j = k + 1; j < i; j++) Hi[j] -= lik * H[j * (j + 1) / 2 + k];
+          Hi[i] -= lik * t;
+          S.rhs[i] -= lik * yk;
+        }
+      } else if (i == k) S.dinv[k] = inv;
     }
-    WSYNC();
-    LANE_FOR(i, NV) { if (i > k) H[i * (i + 1) / 2 + k] *= inv; else if (i == k) S.dinv[k] = inv; }
     WSYNC();
   }
   if (lane == 0) S.dinv[NV - 1] = tsg_rcp(fmax(H[NTRI - 1], MINVAL));
   WSYNC();
-  TSG_UNROLL1
-  for (int k = 0; k < NV - 1; k++) {   // L y = g (unit diagonal)
-    double yk = S.rhs[k];
-    WSYNC();
-    LANE_FOR(i, NV) if (i > k) { double l = H[i * (i + 1) / 2 + k]; if (l != 0.0) S.rhs[i] -= l * yk; }
-    WSYNC();
-  }
-  LANE_FOR(i, NV) S.rhs[i] *= S.dinv[i];
+  LANE_FOR(i, NV) S.rhs[i] *= S.dinv[i];   // z = D^-1 y
   WSYNC();
   TSG_UNROLL1
-  for (int k = NV - 1; k > 0; k--) {   // L^T x = z
+  for (int k = NV - 1; k > 0; k--) {   // L^T x = z with L_ki = t_ki / d_i
     double xk = S.rhs[k];
     WSYNC();
-    LANE_FOR(i, NV) if (i < k) { double l = H[k * (k + 1) / 2 + i]; if (l != 0.0) S.rhs[i] -= l * xk; }
+    LANE_FOR(i, NV) if (i < k) { double t = H[k * (k + 1) / 2 + i]; if (t != 0.0) S.rhs[i] -= t * S.dinv[i] * xk; }
     WSYNC();
   }
   LANE_FOR(i, NV) S.search[i] = -S.rhs[i];
@@ -1115,32 +1111,35 @@ TSG_FN_NOINLINE double newton_direction(int grad_only, double oldcost, double co
     double scale = tsg_div(1.0, m.meaninertia * NV);
     if (scale * (oldcost - cost) < m.tol || scale * tsg_sqrt(gn) < m.tol) return -1.0;
   }
-  // Hessian, packed lower triangle (item = entry)
-  LANE_FOR(e, NTRI) {
-    int i = m.tri_i[e], j = m.tri_j[e];
-    int bi = i / 6, ki = i % 6, bj = j / 6, kj = j % 6;
-    double v = (i == j) ? m.M[i] : 0.0;
-    TSG_UNROLL1
-    for (int n = 0; n < nact; n++) {
-      const Con& k = con_at(S, S.order[n]);
-      if (k.zone == ZONE_TOP) continue;
-      int si = k.b2 == bi ? 1 : (k.b1 == bi ? 0 : -1);
-      int sj = k.b2 == bj ? 1 : (k.b1 == bj ? 0 : -1);
-      if (si < 0 || sj < 0) continue;
-      const double* wt = m.wtab[k.zone == ZONE_MIDDLE ? 1 : 0];
+  // Hessian, packed lower triangle: mass matrix, then one contact at a time adds its own block entries
+  // (21 for a floor contact, 78 for a bar-bar contact) -- no entry is touched by two lanes in a phase
+  LANE_FOR(e, NTRI) S.u.hes.H[e] = (m.tri_i[e] == m.tri_j[e]) ? m.M[m.tri_i[e]] : 0.0;
+  WSYNC();
+  TSG_UNROLL1
+  for (int n = 0; n < nact; n++) {
+    const Con& k = con_at(S, S.order[n]);
+    if (k.zone == ZONE_TOP) continue;
+    const double* wt = m.wtab[k.zone == ZONE_MIDDLE ? 1 : 0];
+    int two = k.b1 >= 0;
+    LANE_FOR(e, two ? 78 : 21) {
+      // local 12x12 (or 6x6) lower triangle: index 0..5 -> side 1 (b2), 6..11 -> side 0 (b1)
+      int li = m.tri_i[e], lj = m.tri_j[e];
+      int si = li < 6 ? 1 : 0, sj = lj < 6 ? 1 : 0, ki = li % 6, kj = lj % 6;
+      int gi = 6 * (si ? k.b2 : k.b1) + ki, gj = 6 * (sj ? k.b2 : k.b1) + kj;
       double ci[6], cj[6], acc = 0;
       Jcol(k, si, ki, ci); Jcol(k, sj, kj, cj);
       for (int r = 0; r < 6; r++) acc += wt[r] * ci[r] * cj[r];
-      v += k.wcoef * acc;
+      double v = k.wcoef * acc;
       if (k.zone == ZONE_MIDDLE) {
         double bi_ = k.bvec[si][ki], bj_ = k.bvec[sj][kj];
         double ai = m.mu * (ci[0] - bi_), aj = m.mu * (cj[0] - bj_);
         v += k.ca * ai * aj - k.cb * bi_ * bj_;
       }
+      int hi = gi > gj ? gi : gj, lo = gi > gj ? gj : gi;
+      S.u.hes.H[hi * (hi + 1) / 2 + lo] += v;
     }
-    S.u.hes.H[e] = v;
+    WSYNC();
   }
-  WSYNC();
   factor_solve(S, lane);
   return gn;
 }
@@ -1201,11 +1200,12 @@ TSG_FN int ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, EnvScrat
 // exact line search along S.search from S.qacc (jar current, S.gauss = current Gauss cost); returns alpha
 TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   CTX_BIND
-  double snorm = 0, qG1 = 0, qG2 = 0;
+  double snorm = 0, qG1 = 0, qG2 = 0, gs = 0;
   TSG_UNROLL1
   for (int k = 0; k < NV; k++) {
     double sk = S.search[k];
     snorm += sk * sk;
+    gs += S.grad[k] * sk;
     qG1 += sk * (m.M[k] * S.qacc[k]) - S.fsm[k] * sk;
     qG2 += 0.5 * sk * (m.M[k] * sk);
   }
@@ -1234,7 +1234,11 @@ TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   }
   WSYNC();
   LsPnt p0, p1, p2, pmid, p1next, p2next;
-  ls_point(p0, 0.0, S, m, c, lane);
+  // alpha = 0 needs no evaluation pass: cost is the current cost, the slope is grad . search and, search being the
+  // Newton direction (H search = -grad), the curvature search' H search = -slope
+  p0.alpha = 0; p0.cost = S.cost; p0.d0 = gs; p0.d1 = -gs > 0 ? -gs : MINVAL;
+  if (lane == 0) S.ls_evals = 1;
+  WSYNC();
   ls_point(p1, p0.alpha - tsg_div(p0.d0, p0.d1), S, m, c, lane);
   if (p0.cost < p1.cost) p1 = p0;
   if (fabs(p1.d0) < gtol) return p1.alpha;
@@ -1303,12 +1307,12 @@ TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int l
     compute_jar(VEC_SMOOTH, CTX_ARGS);
     double cost_sm = total_cost(VEC_SMOOTH, 0, CTX_ARGS);
     compute_jar(VEC_WARM, CTX_ARGS);
-    double cost_ws = total_cost(VEC_WARM, 0, CTX_ARGS);
+    double cost_ws = total_cost(VEC_WARM, 1, CTX_ARGS);   // full: it is the starting point in the common case
     bool use_smooth = cost_ws > cost_sm;
     LANE_FOR(i, NV) S.qacc[i] = use_smooth ? S.asmooth[i] : S.warm[i];
     WSYNC();
-    if (use_smooth) compute_jar(VEC_QACC, CTX_ARGS);
-    cost = total_cost(VEC_QACC, 1, CTX_ARGS);
+    cost = cost_ws;
+    if (use_smooth) { compute_jar(VEC_QACC, CTX_ARGS); cost = total_cost(VEC_QACC, 1, CTX_ARGS); }
   }
   cta_any(S, true);
   if (active) newton_direction(0, 0.0, 0.0, CTX_ARGS);
