@@ -1285,7 +1285,7 @@ TSG_FN void align_sync() { __syncthreads(); }
 #define TSG_ALIGNED 0
 #endif
 TSG_FN bool cta_any(const Scratch& S, bool go) {
-#if TSG_ALIGNED
+#if TSG_ALIGNED && !defined(TSG_ALIGN_SUBSTEP_ONLY)
   if (S.align) return align_any(go);
 #endif
   return go;
@@ -1460,6 +1460,9 @@ TSG_FN_NOINLINE void substep(CTX_PARAMS) {
 // (the SAME barrier primitive as the working warps at every point: a plain and a reducing barrier must not meet)
 TSG_FN void aligned_idle_substep() {
   align_sync();            // simulate: substep start
+#ifdef TSG_ALIGN_SUBSTEP_ONLY
+  return;
+#endif
   align_any(true);         // forward: before stage_constraint
   align_any(true);         // stage_solve: before the warm-start costs
   align_any(true);         // stage_solve: before the first Newton direction
