@@ -110,6 +110,7 @@ struct DevModel {
   // contact
   double K, B, solimp[5], mu, fr[5], dscale[6], fscale[6];
   double wtab[2][6];
+  double solscale;    // 1 / (meaninertia * nv): scale of the solver convergence tests
   double inv_mu2;     // 1 / (mu^2 (1 + mu^2))  // Hessian row weights per zone: bottom = dscale, middle = (0, fr^2)
   // floor
   int floor_type, nrow, ncol, pad2;
@@ -228,12 +229,72 @@ TSG_FN double Jrow_dot_all(const Con& c, int r, const double* v18) {
 // ------------------------------------------------------------------ small math
 // The kernel is instruction-fetch bound (ncu: stall_no_instruction dominates), so the long IEEE fp64 sqrt /
 // divide sequences exist ONCE as out-of-line functions instead of being expanded at every use.
-TSG_FN_NOINLINE double tsg_sqrt(double x) { return sqrt(x); }
-TSG_FN_NOINLINE double tsg_div(double a, double b) { return a / b; }
+TSG_FN_NOINLINE double tsg_div(double a, double b) { return a / b; }   // IEEE; cold call sites (collision geometry)
 #if TSG_DEVICE
 TSG_FN double tsg_rcp(double x) { return __drcp_rn(x); }  // correctly rounded, == 1.0 / x
+// sqrt for the hot call sites: MUFU.RSQ64H seed + two coupled Goldschmidt steps + a final residual correction
+// (<= 1 ulp from the IEEE result; 0 for x == 0 and for subnormal x, which every caller treats as zero anyway).
+// The library sqrt() is a 38-instruction routine whose out-of-line copy also spills callee-saved registers to local
+// memory (ncu: 11 % of the kernel's long-scoreboard stalls); this one is 12 instructions in 6 registers.
+TSG_FN double tsg_sqrt_inl(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  g = fma(fma(-g, g, x), h, g);
+  return x >= 2.2250738585072014e-308 ? g : (x < 0 ? x * __longlong_as_double(0x7ff8000000000000ll) : 0.0);
+}
+TSG_FN_NOINLINE double tsg_sqrt(double x) { return tsg_sqrt_inl(x); }   // out-of-line copy for the colder call sites
+// a / b for the hot call sites (line-search steps, impedance): correctly rounded reciprocal + one residual step
+// (<= 1 ulp from IEEE; callers guarantee a finite non-zero b)
+TSG_FN_NOINLINE double tsg_fdiv(double a, double b) {
+  double r = __drcp_rn(b), q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
 #else
 TSG_FN double tsg_rcp(double x) { return 1.0 / x; }
+TSG_FN double tsg_sqrt(double x) { return sqrt(x); }
+TSG_FN double tsg_sqrt_inl(double x) { return sqrt(x); }
+TSG_FN double tsg_fdiv(double a, double b) { return a / b; }
+#endif
+TSG_FN_NOINLINE double tsg_inv(double x) { return tsg_rcp(x); }  // out-of-line 1 / x for the scattered call sites
+// Sum / any over the lanes of per-lane partial results.  Device: xor butterfly, so every lane ends with the same
+// bits (control flow branches on these values).  Host emulator: the item loop already ran over all items.
+#if TSG_DEVICE
+TSG_FN_NOINLINE double warp_sum(double v) {
+  const unsigned vm = TSG_VMASK();
+#pragma unroll
+  for (int o = TSG_VW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(vm, v, o, TSG_VW);
+  return v;
+}
+TSG_FN_NOINLINE void warp_sum4(double& a, double& b, double& c, double& d) {
+  const unsigned vm = TSG_VMASK();
+#pragma unroll
+  for (int o = TSG_VW / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(vm, a, o, TSG_VW); b += __shfl_xor_sync(vm, b, o, TSG_VW);
+    c += __shfl_xor_sync(vm, c, o, TSG_VW); d += __shfl_xor_sync(vm, d, o, TSG_VW);
+  }
+}
+TSG_FN bool warp_any(bool p) { return __any_sync(TSG_VMASK(), p) != 0; }
+#else
+TSG_FN double warp_sum(double v) { return v; }
+TSG_FN void warp_sum4(double&, double&, double&, double&) {}
+TSG_FN bool warp_any(bool p) { return p; }
+#endif
+// reductions over dofs: lane-parallel partial sums + butterfly (default) or the same loop run by every lane
+#ifdef TSG_NO_WSUM
+#define RED_FOR(i, n) TSG_UNROLL1 for (int i = 0; i < (n); ++i)
+#define RED_SUM(v) (v)
+#define RED_SUM4(a, b, c, d) ((void)0)
+#define RED_ANY(p) (p)
+#else
+#define RED_FOR(i, n) LANE_FOR(i, n)
+#define RED_SUM(v) warp_sum(v)
+#define RED_SUM4(a, b, c, d) warp_sum4(a, b, c, d)
+#define RED_ANY(p) warp_any(p)
 #endif
 TSG_FN double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 TSG_FN void cross3(double* r, const double* a, const double* b) {
@@ -248,7 +309,7 @@ TSG_FN void addscl3(double* r, const double* a, double s) { r[0] += a[0] * s; r[
 TSG_FN double normalize3(double* a) {
   double n = tsg_sqrt(dot3(a, a));
   if (n < MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; }
-  else { double s = tsg_div(1.0, n); a[0] *= s; a[1] *= s; a[2] *= s; }
+  else { double s = tsg_inv(n); a[0] *= s; a[1] *= s; a[2] *= s; }
   return n;
 }
 TSG_FN void mulMV(double* r, const double* R, const double* v) {
@@ -275,7 +336,7 @@ TSG_FN void quat2mat(double* R, const double* q) {
 TSG_FN void normalize4(double* q) {
   double n = tsg_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
-  else if (fabs(n - 1) > MINVAL) { double s = tsg_div(1.0, n); q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+  else if (fabs(n - 1) > MINVAL) { double s = tsg_inv(n); q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
 }
 TSG_FN bool is_bad(double x) { return !(x <= MAXVAL && x >= -MAXVAL); }
 TSG_FN double clampd(double x, double lo, double hi) { return fmin(hi, fmax(lo, x)); }
@@ -422,7 +483,7 @@ TSG_FN bool ccd_eq(double a_, double b_) {
   return (b > a) ? (ab < CCD_EPS * b) : (ab < CCD_EPS * a);
 }
 TSG_FN bool ccd_vec_is_origin(const double* a) { return ccd_eq(a[0], 0) && ccd_eq(a[1], 0) && ccd_eq(a[2], 0); }
-TSG_FN void ccd_normalize(double* v) { double s = tsg_div(1.0, tsg_sqrt(dot3(v, v))); v[0] *= s; v[1] *= s; v[2] *= s; }
+TSG_FN void ccd_normalize(double* v) { double s = tsg_inv(tsg_sqrt(dot3(v, v))); v[0] *= s; v[1] *= s; v[2] *= s; }
 
 TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
   if (o.type == 100) {
@@ -584,7 +645,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
         cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
         sum = b[1] + b[2] + b[3];
       }
-      double inv = tsg_div(1.0, sum), p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+      double inv = tsg_inv(sum), p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
       // v0's second witness is obj2's centre
       for (int i = 0; i < 4; i++) {
         double v2[3];
@@ -888,11 +949,11 @@ TSG_FN double impedance(const DevModel& m, double pos) {
   double d0 = clampd(m.solimp[0], MINIMP, MAXIMP), dw = clampd(m.solimp[1], MINIMP, MAXIMP);
   double width = fmax(MINVAL, m.solimp[2]), mid = clampd(m.solimp[3], MINIMP, MAXIMP), power = fmax(1.0, m.solimp[4]);
   if (d0 == dw || width <= MINVAL) return 0.5 * (d0 + dw);
-  double x = tsg_div(fabs(pos), width), y;
+  double x = tsg_fdiv(fabs(pos), width), y;
   if (x >= 1) return dw;
   if (x == 0) return d0;
   if (power == 1) y = x;
-  else if (power == 2) y = (x <= mid) ? tsg_div(1.0, mid) * (x * x) : 1 - tsg_div(1.0, 1 - mid) * ((1 - x) * (1 - x));
+  else if (power == 2) y = (x <= mid) ? tsg_inv(mid) * (x * x) : 1 - tsg_inv(1 - mid) * ((1 - x) * (1 - x));
   else if (x <= mid) y = (1 / pow(mid, power - 1)) * pow(x, power);
   else y = 1 - (1 / pow(1 - mid, power - 1)) * pow(1 - x, power);
   return d0 + y * (dw - d0);
@@ -940,7 +1001,7 @@ TSG_FN void stage_constraint(Scratch& S, const DevModel& m, int lane) {
     double imp = impedance(m, c.dist);
     if (r == 0) {
       double tran = (c.b1 >= 0 ? m.invw_tran[c.b1] : 0.0) + m.invw_tran[c.b2];
-      c.D0 = tsg_div(1.0, fmax(MINVAL, tsg_div(1 - imp, imp) * tran));
+      c.D0 = tsg_inv(fmax(MINVAL, tsg_fdiv(1 - imp, imp) * tran));
     }
     c.aref[r] = -m.B * vel - (r ? 0.0 : m.K * imp * c.dist);
   }
@@ -967,7 +1028,7 @@ TSG_FN double con_update(Con& c, const DevModel& m, bool full) {
   U[0] = c.jar[0] * mu;
   for (int j = 1; j < 6; j++) { U[j] = c.jar[j] * m.fr[j - 1]; T += U[j] * U[j]; }
   double N = U[0];
-  T = tsg_sqrt(T);
+  T = tsg_sqrt_inl(T);
   if (N >= mu * T || (T <= 0 && N >= 0)) {
     if (full) { for (int j = 0; j < 6; j++) c.force[j] = 0; c.zone = ZONE_TOP; c.wcoef = c.ca = c.cb = 0; }
     return 0;
@@ -984,7 +1045,7 @@ TSG_FN double con_update(Con& c, const DevModel& m, bool full) {
   }
   double Dm = c.D0 * m.inv_mu2, NT = N - mu * T;
   if (full) {
-    double invT = tsg_div(1.0, T);
+    double invT = tsg_inv(T);
     c.force[0] = -Dm * NT * mu;
     double kap = mu * mu - mu * N * invT;
     c.su[0] = 0;
@@ -1008,8 +1069,8 @@ TSG_FN_NOINLINE double total_cost(int which, int full, CTX_PARAMS) {
   double g = 0;
   if (which != VEC_SMOOTH) {
     const double* a = which == VEC_WARM ? S.warm : S.qacc;
-    TSG_UNROLL1
-    for (int k = 0; k < NV; k++) { double d = a[k] - S.asmooth[k]; g += 0.5 * m.M[k] * d * d; }
+    RED_FOR(k, NV) { double d = a[k] - S.asmooth[k]; g += 0.5 * m.M[k] * d * d; }
+    g = RED_SUM(g);
   }
   WSYNC();
   S.gauss = g;
@@ -1035,7 +1096,11 @@ TSG_FN void factor_solve(Scratch& S, int lane) {
         double t = Hi[k];
         if (t != 0.0) {
           double lik = t * inv;
+#ifdef TSG_FACTOR_UNROLL
+          _Pragma("unroll 4")
+#else
           TSG_UNROLL1
+#endif
           for (int j = k + 1; j < i; j++) Hi[j] -= lik * H[j * (j + 1) / 2 + k];
           Hi[i] -= lik * t;
           S.rhs[i] -= lik * yk;
@@ -1088,6 +1153,7 @@ TSG_FN_NOINLINE double newton_direction(int grad_only, double oldcost, double co
     }
   }
   // gradient + qfrc_constraint (item = dof)
+  double gn = 0;
   LANE_FOR(i, NV) {
     int b = i / 6, d = i % 6;
     double f = 0;
@@ -1101,15 +1167,20 @@ TSG_FN_NOINLINE double newton_direction(int grad_only, double oldcost, double co
       for (int r = 0; r < 6; r++) f += col[r] * k.force[r];
     }
     S.fcon[i] = f;
-    S.grad[i] = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
+    double gi = m.M[i] * (S.qacc[i] - S.asmooth[i]) - f;
+    S.grad[i] = gi;
+    gn += gi * gi;
   }
   WSYNC();
-  double gn = 0;
-  TSG_UNROLL1
-  for (int k = 0; k < NV; k++) gn += S.grad[k] * S.grad[k];
+#ifdef TSG_NO_WSUM
+  gn = 0;
+  RED_FOR(k, NV) gn += S.grad[k] * S.grad[k];
+#else
+  gn = warp_sum(gn);
+#endif
   if (grad_only) {  // convergence test of mj_solPrimal: skip the factorisation nobody will use
-    double scale = tsg_div(1.0, m.meaninertia * NV);
-    if (scale * (oldcost - cost) < m.tol || scale * tsg_sqrt(gn) < m.tol) return -1.0;
+    double scale = m.solscale, tg = m.tol * m.meaninertia * NV;
+    if (scale * (oldcost - cost) < m.tol || gn < tg * tg) return -1.0;
   }
   // Hessian, packed lower triangle: mass matrix, then one contact at a time adds its own block entries
   // (21 for a floor contact, 78 for a bar-bar contact) -- no entry is touched by two lanes in a phase
@@ -1157,11 +1228,11 @@ TSG_FN_NOINLINE void ls_eval(double a, CTX_PARAMS) {
     bool bottom = false;
     if (Tsqr <= 0) { if (N < 0) bottom = true; }
     else {
-      double T = tsg_sqrt(Tsqr);
+      double T = tsg_sqrt_inl(Tsqr);
       if (N >= mu * T) {}
       else if (mu * N + T <= 0) bottom = true;
       else {
-        double invT = tsg_div(1.0, T);
+        double invT = tsg_rcp(T);
         double N1 = k.V0, T1 = (k.UV + a * k.VV) * invT;
         double T2 = k.VV * invT - (k.UV + a * k.VV) * T1 * (invT * invT);
         double NT = N - mu * T, Dm = k.D0 * m.inv_mu2;
@@ -1194,21 +1265,21 @@ TSG_FN int ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, EnvScrat
     if (p.d0 < 0 && cand[i].d0 < 0 && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
     else if (p.d0 > 0 && cand[i].d0 > 0 && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
   }
-  if (flag) ls_point(pnext, p.alpha - tsg_div(p.d0, p.d1), S, m, c, lane);
+  if (flag) ls_point(pnext, p.alpha - tsg_fdiv(p.d0, p.d1), S, m, c, lane);
   return flag;
 }
 // exact line search along S.search from S.qacc (jar current, S.gauss = current Gauss cost); returns alpha
 TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   CTX_BIND
   double snorm = 0, qG1 = 0, qG2 = 0, gs = 0;
-  TSG_UNROLL1
-  for (int k = 0; k < NV; k++) {
+  RED_FOR(k, NV) {
     double sk = S.search[k];
     snorm += sk * sk;
     gs += S.grad[k] * sk;
     qG1 += sk * (m.M[k] * S.qacc[k]) - S.fsm[k] * sk;
     qG2 += 0.5 * sk * (m.M[k] * sk);
   }
+  RED_SUM4(snorm, gs, qG1, qG2);
   snorm = tsg_sqrt(snorm);
   if (snorm < MINVAL) return 0;
   double gtol = m.tol * m.ls_tol * snorm * (m.meaninertia * NV);
@@ -1239,7 +1310,7 @@ TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   p0.alpha = 0; p0.cost = S.cost; p0.d0 = gs; p0.d1 = -gs > 0 ? -gs : MINVAL;
   if (lane == 0) S.ls_evals = 1;
   WSYNC();
-  ls_point(p1, p0.alpha - tsg_div(p0.d0, p0.d1), S, m, c, lane);
+  ls_point(p1, p0.alpha - tsg_fdiv(p0.d0, p0.d1), S, m, c, lane);
   if (p0.cost < p1.cost) p1 = p0;
   if (fabs(p1.d0) < gtol) return p1.alpha;
   int dir = p1.d0 < 0 ? 1 : -1, p2update = 0;
@@ -1247,12 +1318,12 @@ TSG_FN_NOINLINE double line_search(CTX_PARAMS) {
   TSG_UNROLL1
   while (p1.d0 * dir <= -gtol && S.ls_evals < m.ls_iterations) {
     p2 = p1; p2update = 1;
-    ls_point(p1, p1.alpha - tsg_div(p1.d0, p1.d1), S, m, c, lane);
+    ls_point(p1, p1.alpha - tsg_fdiv(p1.d0, p1.d1), S, m, c, lane);
     if (fabs(p1.d0) < gtol) return p1.alpha;
   }
   if (S.ls_evals >= m.ls_iterations || !p2update) return p1.alpha;
   p2next = p1;
-  ls_point(p1next, p1.alpha - tsg_div(p1.d0, p1.d1), S, m, c, lane);
+  ls_point(p1next, p1.alpha - tsg_fdiv(p1.d0, p1.d1), S, m, c, lane);
   TSG_UNROLL1
   while (S.ls_evals < m.ls_iterations) {
     ls_point(pmid, 0.5 * (p1.alpha + p2.alpha), S, m, c, lane);
@@ -1370,7 +1441,7 @@ TSG_FN void stage_integrate(Scratch& S, const DevModel& m, int lane) {
       double s = Aj[j];
       TSG_UNROLL1
       for (int k = 0; k < j; k++) s -= Aj[k] * Aj[k];
-      double inv = tsg_div(1.0, tsg_sqrt(s));
+      double inv = tsg_inv(tsg_sqrt(s));
       Aj[j] = inv;  // store 1 / L_jj
       TSG_UNROLL1
       for (int i = j + 1; i < 6; i++) {
@@ -1436,13 +1507,14 @@ TSG_FN_NOINLINE void substep(CTX_PARAMS) {
   CTX_BIND
   // mj_checkPos / mj_checkVel
   bool bad = false;
-  for (int i = 0; i < NQ; i++) bad |= is_bad(S.qpos[i]);
-  for (int i = 0; i < NV; i++) bad |= is_bad(S.qvel[i]);
+  RED_FOR(i, NQ + NV) bad |= is_bad(i < NQ ? S.qpos[i] : S.qvel[i - NQ]);
+  bad = RED_ANY(bad);
   WSYNC();
   if (bad) { if (lane == 0) S.bad |= 1; reset_data(S, m, lane); }
   forward(CTX_ARGS);
   bad = false;
-  for (int i = 0; i < NV; i++) bad |= is_bad(S.qacc[i]);  // mj_checkAcc
+  RED_FOR(i, NV) bad |= is_bad(S.qacc[i]);  // mj_checkAcc
+  bad = RED_ANY(bad);
   WSYNC();
   if (bad) {  // the repeated forward pass runs unaligned: its CTA barriers have no partners
     int al = S.align;

@@ -72,6 +72,7 @@ inline std::string make_dev_model(const TsgModel& t, DevModel& m, const float* h
   for (int k = 0; k < 5; k++) { m.solimp[k] = t.solimp[k]; m.fr[k] = t.friction[k]; }
   m.mu = t.friction[0] / sqrt(t.impratio);
   m.inv_mu2 = 1.0 / (m.mu * m.mu * (1 + m.mu * m.mu));
+  m.solscale = 1.0 / (m.meaninertia * NV);
   m.dscale[0] = 1; m.fscale[0] = m.mu;
   for (int j = 1; j < 6; j++) {
     // R_j = (R_0 / impratio) * f0^2 / f_{j-1}^2  ->  D_j = D_0 * dscale_j
