@@ -270,7 +270,7 @@ TSG_FN_NOINLINE double warp_sum(double v) {
   for (int o = TSG_VW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(vm, v, o, TSG_VW);
   return v;
 }
-TSG_FN_NOINLINE void warp_sum4(double& a, double& b, double& c, double& d) {
+TSG_FN void warp_sum4(double& a, double& b, double& c, double& d) {   // one call site (line_search): inline, the arguments stay in registers
   const unsigned vm = TSG_VMASK();
 #pragma unroll
   for (int o = TSG_VW / 2; o > 0; o >>= 1) {
