@@ -104,7 +104,7 @@ def test_philox_draws_are_keyed_by_env_and_reset_count():
 
 
 def test_contact_spill_path(oracle):
-    """two bars pressed flat into the floor: 19 contacts, i.e. 16 beyond the shared-memory slots (MAXC_S = 3)
+    """two bars pressed flat into the floor: 19 contacts, i.e. 17 beyond the shared-memory slots (MAXC_S = 2)
     that live in the per-warp spill area; results must still match the dense oracle."""
     mj, em = oracle.MjLike("flat"), E.Emul("flat", reverse=True)
     q = []
