@@ -103,6 +103,16 @@ int tsg_step(TsgHandle *h, const void *ctrl_dev, int ctrl_dtype, double *obs_dev
              double *reward_dev, uint8_t *done_dev, double *info_dev, int auto_reset, unsigned long long seed,
              double *term_obs_dev, void *stream);
 
+/* Observation noise (TsgEnvConfig.use_obs_noise; tr_env.py:524-527): tsg_step / tsg_reset then return the NOISY
+ * observation, as the reference does.  real_obs_dev (optional, [n_envs][obs_dim] f64, device) additionally receives
+ * the noise-free observation of every step -- the reference's info["real_observation"] (tr_env.py:505).  The
+ * normal draws are Philox(seed, env id, reset count, episode step): reproducible, unlike the reference's unseeded
+ * np.random.default_rng() (tr_env.py:552).  The handle owns a default buffer (read it with tsg_get_real_obs_host);
+ * pass a device buffer to have the rows written there instead (it must outlive the calls), NULL to switch back. */
+int tsg_set_real_obs(TsgHandle *h, double *real_obs_dev);
+/* the noise-free observations of the last step / reset, HOST buffer [n_envs][obs_dim] (synchronous) */
+int tsg_get_real_obs_host(TsgHandle *h, double *real_obs);
+
 /* mj_forward on the stored states: refreshes the kinematics-derived bookkeeping, optional obs/info */
 int tsg_forward(TsgHandle *h, double *obs_dev, double *info_dev, void *stream);
 

@@ -144,6 +144,12 @@ typedef struct TsgEnvConfig {
   double waypt_reward_amplitude, waypt_reward_stdev; /* tr_env.py:169-170 */
   double kill_force;           /* 1500: tr_env.py:480 */
   double reset_pose[TSG_NPOSE][TSG_NQ];
+  /* observation noise (tr_env.py:142,161-162,552-644): obs = real_obs + N(0, stdev) per component, the tracking
+   * vector / yaw re-derived from the noisy cap positions; rewards and termination always use the true state */
+  int32_t use_obs_noise;
+  int32_t pad_noise_;
+  double obs_noise_tendon_stdev;  /* 0.02 */
+  double obs_noise_cap_pos_stdev; /* 0.05: end-cap positions AND end-cap velocities (tr_env.py:606-617) */
 } TsgEnvConfig;
 
 /* draws consumed by one reset (reference: unseeded numpy, tr_env.py:730,775,802-804,831-832) */

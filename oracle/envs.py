@@ -65,7 +65,23 @@ class OracleEnv:
         v = left - right
         return np.arctan2(-v[0], v[1])
 
-    # ---- observation
+    # ---- observation noise (tr_env.py:552-644); z = the standard-normal draws, one per noisy component, in
+    # observation order [cap positions 18, cap velocities 18 (if used), tendon lengths 9]
+    def noisy_obs(self, obs, z):
+        c = self.cfg
+        n = 27 + (18 if c.use_cap_velocity else 0)
+        z = np.asarray(z, np.float64)[:n]
+        out = np.array(obs, np.float64)
+        sp, st = c.obs_noise_cap_pos_stdev, c.obs_noise_tendon_stdev
+        out[:n - 9] = z[:n - 9] * sp + out[:n - 9]          # cap positions :554-565, cap velocities :606-617 (same stdev)
+        out[n - 9:n] = z[n - 9:] * st + out[n - 9:n]         # tendon lengths :575-576
+        if self.task in ("tracking", "aiming"):                # :626-639
+            centre_noise = out[:18].reshape(6, 3).sum(axis=0) / 6
+            tv = obs[n:n + 2] - centre_noise[:2]
+            d = tv / np.linalg.norm(tv)
+            out[n:n + 3] = [tv[0], tv[1], np.arctan2(d[1], d[0])]
+        return out
+
     def get_obs(self):
         mj = self.mj
         if self.legacy:

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(c
 }
 
 // Hand ready pool slots to envs that are done (one CTA; ordered, hence deterministic: the k-th done env gets the
-// k-th ready slot).  Copies record (all but the env's own reset counter), heading ring and reset observation;
+// k-th ready slot).  Copies record (all but the env's own reset counter, which is incremented), heading ring and reset observation;
 // the slot restarts from phase 0 with its next draw.  Done envs left without a slot are flagged in need_sync.
 __global__ void __launch_bounds__(1024) tsg_assign_kernel(double* __restrict__ state, double* __restrict__ heading,
                                                            const uint8_t* __restrict__ done, uint8_t* __restrict__ need_sync,
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(1024) tsg_assign_kernel(double* __restrict__ s
       if (obs) { if (term_obs) term_obs[(size_t)e * obs_dim + i] = obs[(size_t)e * obs_dim + i]; obs[(size_t)e * obs_dim + i] = v; }
       if (obs32) obs32[(size_t)e * obs_dim + i] = (float)v;
     }
-    if (lane == 0) { src[SO_FLAGS] = 0; src[SO_NRESET] += 1; if (need_sync) need_sync[e] = 0; }
+    if (lane == 0) { src[SO_FLAGS] = 0; src[SO_NRESET] += 1; dst[SO_NRESET] += 1; if (need_sync) need_sync[e] = 0; }
   }
 }
 
@@ -205,6 +205,8 @@ struct TsgHandle {
   uint8_t* d_mask;
   Con* d_spill; int* d_counter;
   double* d_pool_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
+  double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
+  double* d_realobs_own;
   int grid[3];
   cudaStream_t own_stream;
 };
@@ -301,6 +303,11 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
   CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_VWARPS * (MAXC - MAXC_S) * sizeof(Con)));
   CK(cudaMalloc(&h->d_counter, 2 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  if (ec.use_obs_noise) {   // the noise-free observation always has a home; tsg_set_real_obs redirects it
+    CK(cudaMalloc(&h->d_realobs_own, (size_t)n_envs * ec.obs_dim * sizeof(double)));
+    CK(cudaMemset(h->d_realobs_own, 0, (size_t)n_envs * ec.obs_dim * sizeof(double)));
+    h->real_obs = h->d_realobs_own;
+  }
   if (n_pool) {
     CK(cudaMalloc(&h->d_pool_obs, (size_t)n_pool * ec.obs_dim * sizeof(double)));
     CK(cudaMalloc(&h->d_lists, (size_t)2 * n_pool * sizeof(int)));
@@ -319,7 +326,7 @@ int tsg_destroy(TsgHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
-                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter, h->d_pool_obs, h->d_lists, h->d_counts, h->d_need_sync};
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter, h->d_pool_obs, h->d_lists, h->d_counts, h->d_need_sync, h->d_realobs_own};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -355,6 +362,7 @@ static StepIO base_io(TsgHandle* h) {
   io.state = h->d_state; io.heading = h->d_heading; io.draws = h->d_draws;
   io.n_envs = h->n_envs; io.env_id_base = h->env_id_base;
   io.n_pool = h->n_pool; io.pool_obs = h->d_pool_obs;
+  io.real_obs = h->real_obs;
   return io;
 }
 
@@ -402,6 +410,20 @@ int tsg_step(TsgHandle* h, const void* ctrl_dev, int ctrl_dtype, double* obs_dev
     rc = launch_env<MODE_RESET>(h, r, s);
   }
   return rc;
+}
+
+int tsg_set_real_obs(TsgHandle* h, double* real_obs_dev) {
+  if (!h) FAIL("tsg_set_real_obs: null handle");
+  if (!h->d_realobs_own) FAIL("tsg_set_real_obs: the handle was created without use_obs_noise");
+  h->real_obs = real_obs_dev ? real_obs_dev : h->d_realobs_own;
+  return 0;
+}
+int tsg_get_real_obs_host(TsgHandle* h, double* real_obs) {
+  if (!h || !real_obs) FAIL("tsg_get_real_obs_host: null argument");
+  if (!h->real_obs) FAIL("tsg_get_real_obs_host: the handle was created without use_obs_noise");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(real_obs, h->real_obs, (size_t)h->n_envs * h->obs_dim * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int tsg_forward(TsgHandle* h, double* obs_dev, double* info_dev, void* stream) {

@@ -123,12 +123,13 @@ struct DevModel {
 
 struct EnvCfg {
   int env_kind, task, frame_skip, obs_dim, use_cap_velocity, terminate_when_unhealthy, is_test;
-  int reward_delay_steps, max_episode_steps, warmup_steps, npose, pad;
+  int reward_delay_steps, max_episode_steps, warmup_steps, npose, use_obs_noise;
   double desired_direction, ctrl_cost_weight, healthy_reward, yaw_reward_weight;
   double min_reset_heading, max_reset_heading;
   double tendon_reset_mean, tendon_reset_stdev, tendon_min_length, tendon_max_length;
   double waypt_range[2], waypt_angle_range[2];
   double ditch_reward_max, ditch_reward_stdev, waypt_reward_amplitude, waypt_reward_stdev, kill_force, dt;
+  double obs_noise_tendon_stdev, obs_noise_cap_pos_stdev;
   double reset_pose[6][NQ];
 };
 
@@ -1097,12 +1098,9 @@ TSG_FN void factor_solve(Scratch& S, int lane) {
         double t = Hi[k];
         if (t != 0.0) {
           double lik = t * inv;
-#ifdef TSG_FACTOR_UNROLL
-          _Pragma("unroll 4")
-#else
+          int o = (k + 1) * (k + 2) / 2 + k;   // H[j][k], j = k + 1, ...
           TSG_UNROLL1
-#endif
-          for (int j = k + 1; j < i; j++) Hi[j] -= lik * H[j * (j + 1) / 2 + k];
+          for (int j = k + 1; j < i; j++) { Hi[j] -= lik * H[o]; o += j + 1; }
           Hi[i] -= lik * t;
           S.rhs[i] -= lik * yk;
         }
@@ -1116,8 +1114,7 @@ TSG_FN void factor_solve(Scratch& S, int lane) {
   WSYNC();
   TSG_UNROLL1
   for (int k = NV - 1; k > 0; k--) {   // L^T x = z with L_ki = t_ki / d_i
-    double xk = S.rhs[k];
-    WSYNC();
+    double xk = S.rhs[k];   // final: rows > k were substituted in earlier steps, one barrier per step is enough
     LANE_FOR(i, NV) if (i < k) { double t = H[k * (k + 1) / 2 + i]; if (t != 0.0) S.rhs[i] -= t * S.dinv[i] * xk; }
     WSYNC();
   }

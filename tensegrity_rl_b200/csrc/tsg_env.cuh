@@ -75,6 +75,72 @@ TSG_FN void mat2quat_scipy(const double* M, double* q) {
   for (int i = 0; i < 4; i++) q[i] /= n;
 }
 
+// Philox4x32-10, counter = (env id, reset count), key = seed
+TSG_FN void philox(unsigned long long seed, unsigned long long ctr_lo, unsigned long long ctr_hi, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+TSG_FN double u01(uint32_t a, uint32_t b) {  // 53-bit uniform in [0,1)
+  unsigned long long x = (((unsigned long long)a << 32) | b) >> 11;
+  return (double)x * (1.0 / 9007199254740992.0);
+}
+// Observation noise (tr_env.py:552-644).  S.u.post.obs holds the true observation on entry and the noisy one on
+// return: every component of the cap positions / cap velocities gets N(0, obs_noise_cap_pos_stdev), every tendon
+// length N(0, obs_noise_tendon_stdev); the tracking vector loses the mean cap-position noise and the target yaw is
+// re-derived from it (:626-639); the vel_track command is passed through (:641-644).  Normals: Philox keyed by
+// (seed, stream id, reset count, episode step, pair index) + Box-Muller, one pair per lane; they are staged in the
+// implicit-damping scratch, which is dead at this point.
+// the pr-th pair of standard normals of one observation (Philox + Box-Muller)
+TSG_FN void noise_pair(unsigned long long seed, unsigned long long stream, unsigned long long nreset,
+                       unsigned long long step, int pr, double& z0, double& z1) {
+  uint32_t r[4];
+  philox(seed ^ 0x6f62736e6f697365ull, stream, (((nreset << 24) | (step & 0xffffffull)) << 8) | (unsigned long long)pr, r);
+  double u1 = 1.0 - u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+  double rad = sqrt(-2.0 * log(u1));
+  z0 = rad * cos(2 * PI * u2); z1 = rad * sin(2 * PI * u2);
+}
+TSG_FN_NOINLINE void obs_noise(unsigned long long seed, unsigned long long stream, unsigned long long nreset,
+                               unsigned long long step, CTX_PARAMS) {
+  CTX_BIND
+  const int nvel = c.use_cap_velocity ? 18 : 0, n = 27 + nvel;
+  double* z = &S.u.post.Dblk[0][0];
+  LANE_FOR(pr, (n + 1) / 2) {
+    double z0, z1;
+    noise_pair(seed, stream, nreset, step, pr, z0, z1);
+    z[2 * pr] = z0;
+    if (2 * pr + 1 < n) z[2 * pr + 1] = z1;
+  }
+  WSYNC();
+  const double sp = c.obs_noise_cap_pos_stdev, st = c.obs_noise_tendon_stdev;
+  double cn0 = 0, cn1 = 0;   // mean of the noisy centroid-relative cap positions (x, y)
+  for (int cap = 0; cap < 6; cap++) {
+    cn0 += sp * z[3 * cap] + S.u.post.obs[3 * cap];
+    cn1 += sp * z[3 * cap + 1] + S.u.post.obs[3 * cap + 1];
+  }
+  cn0 /= 6; cn1 /= 6;
+  WSYNC();
+  LANE_FOR(i, n) S.u.post.obs[i] = (i < 18 + nvel ? sp : st) * z[i] + S.u.post.obs[i];
+  if ((c.task == TASK_TRACKING || c.task == TASK_AIMING) && lane == 0) {
+    double tx = S.u.post.obs[n] - cn0, ty = S.u.post.obs[n + 1] - cn1, nn = sqrt(tx * tx + ty * ty);
+    S.u.post.obs[n] = tx; S.u.post.obs[n + 1] = ty; S.u.post.obs[n + 2] = atan2(ty / nn, tx / nn);
+  }
+  WSYNC();
+}
+// true observation -> io.real_obs row (if registered), then the noise
+#define TSG_OBS_NOISE(row, stream, nreset, step)                                                                     \
+  if (c.use_obs_noise) {                                                                                              \
+    if (io.real_obs && (row) >= 0) { LANE_FOR(i_, c.obs_dim) io.real_obs[(size_t)(row) * c.obs_dim + i_] = S.u.post.obs[i_]; } \
+    WSYNC();                                                                                                          \
+    obs_noise(io.seed, (unsigned long long)(stream), (unsigned long long)(nreset), (unsigned long long)(step), CTX_ARGS); \
+  }
+
 // observation into S.obs (stale positions / tendon lengths, fresh qvel)
 TSG_FN void compute_obs(EnvScratch& S, const DevModel& m, const EnvCfg& c, const Aux& A, int lane) {
   if (c.env_kind == ENV_LEGACY) {
@@ -381,6 +447,7 @@ struct StepIO {
   int explicit_draws;
   int n_pool;           // background reset pool slots stored after the n_envs records
   double* pool_obs;     // [n_pool][obs_dim]: reset observation of each ready pool slot
+  double* real_obs;     // [N][obs_dim] or null: noise-free observation when use_obs_noise (info["real_observation"])
 };
 
 TSG_FN void write_obs(const EnvScratch& S, const EnvCfg& c, const StepIO& io, int e, int lane) {
@@ -398,6 +465,7 @@ TSG_FN void run_step(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
   env_step(A, O, CTX_ARGS);
   compute_obs(S, m, c, A, lane);
   A.ep_len += 1; A.ep_ret += O.reward;
+  TSG_OBS_NOISE(e, io.env_id_base + e, io.state[(size_t)e * STATE_STRIDE + SO_NRESET], A.ep_len)
   int truncated = (c.max_episode_steps > 0 && A.ep_len >= c.max_episode_steps) ? 1 : 0;
   write_obs(S, c, io, e, lane);
   if (lane == 0) {
@@ -440,22 +508,6 @@ TSG_FN void run_step(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
   store_env(S, A, io.state + (size_t)e * STATE_STRIDE, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
 }
 
-// Philox4x32-10, counter = (env id, reset count), key = seed
-TSG_FN void philox(unsigned long long seed, unsigned long long ctr_lo, unsigned long long ctr_hi, uint32_t out[4]) {
-  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  for (int r = 0; r < 10; r++) {
-    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
-    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-TSG_FN double u01(uint32_t a, uint32_t b) {  // 53-bit uniform in [0,1)
-  unsigned long long x = (((unsigned long long)a << 32) | b) >> 11;
-  return (double)x * (1.0 / 9007199254740992.0);
-}
 TSG_FN void make_draws(double* d, unsigned long long seed, unsigned long long env_id, unsigned long long nreset) {
   double un[12];
   for (int k = 0; k < 6; k++) {
@@ -488,6 +540,7 @@ TSG_FN void run_reset(EnvScratch& S, const DevModel& m, const EnvCfg& c, const S
   WSYNC();
   env_reset(S, m, c, A, lane);
   compute_obs(S, m, c, A, lane);
+  TSG_OBS_NOISE(e, io.env_id_base + e, nreset + 1, 0)
   write_obs(S, c, io, e, lane);
   store_env(S, A, rec, io.heading + (size_t)e * HEADING_SLOTS, need_head, lane);
   if (lane == 0) rec[SO_NRESET] = nreset + 1;
@@ -527,6 +580,7 @@ TSG_FN void run_pool(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
   if (phase >= c.warmup_steps) {
     reset_finish(S, m, c, A, lane);
     compute_obs(S, m, c, A, lane);
+    TSG_OBS_NOISE(-1, (1ull << 40) + (unsigned long long)(io.env_id_base + p), nreset + 1, 0)
     LANE_FOR(i, c.obs_dim) io.pool_obs[(size_t)p * c.obs_dim + i] = S.u.post.obs[i];
     phase = c.warmup_steps + 1;
   }

@@ -115,6 +115,10 @@ inline std::string make_env_cfg(const TsgEnvConfig& t, const TsgModel& mod, EnvC
   c.ditch_reward_max = t.ditch_reward_max; c.ditch_reward_stdev = t.ditch_reward_stdev;
   c.waypt_reward_amplitude = t.waypt_reward_amplitude; c.waypt_reward_stdev = t.waypt_reward_stdev;
   c.kill_force = t.kill_force;
+  c.use_obs_noise = t.use_obs_noise ? 1 : 0;
+  c.obs_noise_tendon_stdev = t.obs_noise_tendon_stdev; c.obs_noise_cap_pos_stdev = t.obs_noise_cap_pos_stdev;
+  if (c.use_obs_noise && c.env_kind != ENV_TR) return "use_obs_noise exists for tr_env only";
+  if (c.use_obs_noise && (c.obs_noise_tendon_stdev < 0 || c.obs_noise_cap_pos_stdev < 0)) return "negative obs noise stdev";
   c.dt = mod.timestep * t.frame_skip;
   for (int p = 0; p < TSG_NPOSE; p++) for (int k = 0; k < NQ; k++) c.reset_pose[p][k] = t.reset_pose[p][k];
   return "";

@@ -61,11 +61,13 @@ class _SingleEnv:
                  max_episode_steps=0, render_mode=None, **kwargs):
         self.L = _lib.load()
         for k in ("width", "height", "camera_id", "camera_name", "use_contact_forces", "contact_cost_weight",
-                  "contact_force_range", "reset_noise_scale", "contact_with_self_penalty", "use_obs_noise",
-                  "use_cap_size_noise", "obs_noise_tendon_stdev", "obs_noise_cap_pos_stdev", "cap_size_noise_range",
-                  "threshold_waypt"):
+                  "contact_force_range", "reset_noise_scale", "contact_with_self_penalty",
+                  "use_cap_size_noise", "cap_size_noise_range", "threshold_waypt"):
             v = kwargs.pop(k, None)
-            if k in ("use_contact_forces", "use_obs_noise", "use_cap_size_noise") and v:
+            if k == "use_cap_size_noise" and v:   # tr_env.py:685-706 calls model.geom_names / geom_name2id, which the
+                # `mujoco` 2.3.7 bindings do not have (mujoco-py API): the reference itself raises AttributeError here
+                raise NotImplementedError("use_cap_size_noise=True fails in the reference too (mujoco-py-only API, tr_env.py:689-699)")
+            if k == "use_contact_forces" and v:
                 raise NotImplementedError(f"{k}=True is off in the reference defaults and not built (SURVEY 8f rank 4)")
             if k == "reset_noise_scale" and v:
                 raise NotImplementedError("reset_noise_scale != 0 is not built")
@@ -128,7 +130,12 @@ class _SingleEnv:
             "forward_reward": float(row[I["rew_fwd"]]),
         }
         if self.env_kind == "tr_env":
-            info.update(tendon_length=np.array(row[I["ten"]:I["ten"] + 9]), real_observation=obs.copy(),
+            real = obs.copy()
+            if self.cfg.use_obs_noise:   # obs is the noisy observation (tr_env.py:524-527), info carries the true one (:505)
+                buf = np.zeros((1, self.obs_dim))
+                _lib.check(self.L.tsg_get_real_obs_host(self.h, self._p(buf)))
+                real = buf[0]
+            info.update(tendon_length=np.array(row[I["ten"]:I["ten"] + 9]), real_observation=real,
                         waypt=np.array(row[I["waypt"]:I["waypt"] + 2]) if self.cfg.task in (2, 3) else np.array([]),
                         oripoint=np.array(row[I["ori"]:I["ori"] + 2]))
         bf = float(row[I["barforce"]])

@@ -15,7 +15,7 @@ INFO = dict(rew_fwd=0, rew_ctrl=1, rew_survive=2, x=3, y=4, psi=5, xvel=6, yvel=
 SYMBOLS = ["tsg_last_error", "tsg_version", "tsg_device_count", "tsg_create", "tsg_create_pooled", "tsg_pool_stats_host", "tsg_destroy", "tsg_num_envs",
            "tsg_obs_dim", "tsg_launches", "tsg_kernel_config", "tsg_reset", "tsg_step", "tsg_forward",
            "tsg_get_state_host", "tsg_set_state_host", "tsg_get_records_host", "tsg_set_records_host",
-           "tsg_get_draws_host", "tsg_step_host", "tsg_reset_host"]
+           "tsg_get_draws_host", "tsg_step_host", "tsg_reset_host", "tsg_set_real_obs", "tsg_get_real_obs_host"]
 
 
 class TsgError(RuntimeError):
@@ -53,6 +53,8 @@ def load():
     L.tsg_get_draws_host.argtypes = [vp, dp]
     L.tsg_step_host.argtypes = [vp, dp, dp, dp, u8p, dp, C.c_int, C.c_ulonglong, dp]
     L.tsg_reset_host.argtypes = [vp, u8p, C.c_ulonglong, dp, dp]
+    L.tsg_set_real_obs.argtypes = [vp, dp]
+    L.tsg_get_real_obs_host.argtypes = [vp, dp]
     _lib = L
     return L
 

@@ -67,6 +67,7 @@ class TsgEnvConfig(C.Structure):
         ("waypt_range", d * 2), ("waypt_angle_range", d * 2),
         ("ditch_reward_max", d), ("ditch_reward_stdev", d), ("waypt_reward_amplitude", d), ("waypt_reward_stdev", d),
         ("kill_force", d), ("reset_pose", (d * NQ) * NPOSE),
+        ("use_obs_noise", i32), ("pad_noise_", i32), ("obs_noise_tendon_stdev", d), ("obs_noise_cap_pos_stdev", d),
     ]
 
 
@@ -375,7 +376,8 @@ def env_config(md, env_kind="tr_env", desired_action="straight", desired_directi
                tendon_reset_mean=None, tendon_reset_stdev=None, tendon_max_length=None, tendon_min_length=-0.45,
                way_pts_range=(2.5, 3.5), way_pts_angle_range=(-math.pi / 6, math.pi / 6),
                ditch_reward_max=300, ditch_reward_stdev=0.15, waypt_reward_amplitude=100, waypt_reward_stdev=0.10,
-               yaw_reward_weight=1, max_episode_steps=5000, frame_skip=20, warmup_steps=50):
+               yaw_reward_weight=1, max_episode_steps=5000, frame_skip=20, warmup_steps=50,
+               use_obs_noise=False, obs_noise_tendon_stdev=0.02, obs_noise_cap_pos_stdev=0.05):
     """Defaults per env: tr_env.py:137-173 / tensegrity_env.py:160-181."""
     legacy = env_kind in ("tensegrity_env", ENV_LEGACY)
     c = TsgEnvConfig()
@@ -414,6 +416,10 @@ def env_config(md, env_kind="tr_env", desired_action="straight", desired_directi
     c.ditch_reward_max, c.ditch_reward_stdev = ditch_reward_max, ditch_reward_stdev
     c.waypt_reward_amplitude, c.waypt_reward_stdev = waypt_reward_amplitude, waypt_reward_stdev
     c.kill_force = 1500.0
+    if use_obs_noise and legacy:
+        raise ValueError("use_obs_noise is a tr_env option (tr_env.py:142)")
+    c.use_obs_noise = int(bool(use_obs_noise))          # tr_env.py:142,236
+    c.obs_noise_tendon_stdev, c.obs_noise_cap_pos_stdev = obs_noise_tendon_stdev, obs_noise_cap_pos_stdev   # :161-162
     poses = np.zeros((NPOSE, NQ))
     if legacy:
         c.npose = 1

@@ -68,6 +68,10 @@ class TensegrityVecEnv:
             self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.info = torch.zeros(n, _lib.INFO_DIM, dtype=torch.float64, device=dev)
             self.term_obs = torch.zeros(n, self.obs_dim, dtype=torch.float64, device=dev)
+            self.real_obs = None
+            if self.cfg.use_obs_noise:   # obs rows are noisy (tr_env.py:524-527); the true ones land here
+                self.real_obs = torch.zeros(n, self.obs_dim, dtype=torch.float64, device=dev)
+                _lib.check(self.L.tsg_set_real_obs(self.h, _ptr(self.real_obs)))
         self._actions = None
         self.n_steps = 0
 
@@ -126,9 +130,10 @@ class TensegrityVecEnv:
         obs_h, rew_h, done_h, info_h = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool), self.info.cpu().numpy()
         full = self.info_mode == "full" or (self.info_mode == "auto" and self.num_envs <= 64)
         term_h = self.term_obs.cpu().numpy() if (self.auto_reset and done_h.any()) else None
+        real_h = self.real_obs.cpu().numpy() if (full and self.real_obs is not None) else obs_h
         infos = []
         for e in range(self.num_envs):
-            d = self.info_dict(info_h[e], obs_h[e]) if full else {}
+            d = self.info_dict(info_h[e], real_h[e]) if full else {}
             if done_h[e]:
                 d["TimeLimit.truncated"] = bool(info_h[e, _lib.INFO["truncated"]]) and not bool(info_h[e, _lib.INFO["terminated"]])
                 if term_h is not None:

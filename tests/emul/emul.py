@@ -87,6 +87,19 @@ class Emul:
                           C.c_ulonglong(seed), C.c_longlong(env_id), P(self.obs))
         return self.obs.copy()
 
+    def set_noise(self, seed, env_id=0):
+        """observation-noise keys; the true observation of every step / reset then lands in self.real_obs"""
+        self.real_obs = np.zeros(self.cfg.obs_dim)
+        self.L.emul_set_noise(self.h, C.c_ulonglong(seed), C.c_longlong(env_id), P(self.real_obs))
+
     def forward(self):
         self.L.emul_forward(self.h, P(self.rec), P(self.heading), P(self.obs), P(self.info))
         return self.obs.copy(), self.info.copy()
+
+
+def obs_normals(seed, stream, nreset, step, n, reverse=False):
+    """the standard-normal draws the CUDA source uses for the observation of (stream, reset count, episode step)"""
+    out = np.zeros(n + 1)
+    lib(reverse).emul_obs_normals(C.c_ulonglong(seed), C.c_ulonglong(stream), C.c_ulonglong(nreset), C.c_ulonglong(step),
+                                  int(n), P(out))
+    return out[:n]

@@ -15,6 +15,7 @@ struct Emul {
   float* hdata;
   EnvScratch S;
   Con spill[MAXC - MAXC_S];
+  unsigned long long seed; long long env_id; double* real_obs;   // observation-noise keys / true-observation output
 };
 
 extern "C" {
@@ -33,30 +34,45 @@ const char* emul_create(const TsgModel* model, const TsgEnvConfig* cfg, void** o
   if (!err.empty()) { delete E; return err.c_str(); }
   memset(&E->S, 0, sizeof(E->S));
   E->S.spill = E->spill;
+  E->seed = 0; E->env_id = 0; E->real_obs = nullptr;
   *out = E;
   return nullptr;
 }
 void emul_destroy(void* h) { Emul* E = (Emul*)h; free(E->hdata); delete E; }
 int emul_scratch_bytes() { return (int)sizeof(EnvScratch); }
 
-static StepIO make_io(double* rec, double* heading) {
+static StepIO make_io(double* rec, double* heading, const Emul* E = nullptr) {
   StepIO io;
   memset(&io, 0, sizeof(io));
   io.state = rec; io.heading = heading; io.n_envs = 1;
+  if (E) { io.seed = E->seed; io.env_id_base = E->env_id; io.real_obs = E->real_obs; }
   return io;
+}
+void emul_set_noise(void* h, unsigned long long seed, long long env_id, double* real_obs) {
+  Emul* E = (Emul*)h; E->seed = seed; E->env_id = env_id; E->real_obs = real_obs;
+}
+void emul_obs_normals(unsigned long long seed, unsigned long long stream, unsigned long long nreset,
+                      unsigned long long step, int n, double* out) {
+  for (int pr = 0; pr < (n + 1) / 2; pr++) {
+    double z0, z1;
+    noise_pair(seed, stream, nreset, step, pr, z0, z1);
+    out[2 * pr] = z0;
+    if (2 * pr + 1 < n) out[2 * pr + 1] = z1;
+  }
 }
 void emul_step(void* h, double* rec, double* heading, const double* ctrl, double* obs, double* reward,
                uint8_t* done, double* info) {
   Emul* E = (Emul*)h;
-  StepIO io = make_io(rec, heading);
+  StepIO io = make_io(rec, heading, E);
   io.ctrl64 = ctrl; io.obs = obs; io.reward = reward; io.done = done; io.info = info;
   run_step(E->S, E->m, E->c, io, 0, 0);
 }
 void emul_reset(void* h, double* rec, double* heading, double* draws, int explicit_draws, unsigned long long seed,
                 long long env_id, double* obs) {
   Emul* E = (Emul*)h;
-  StepIO io = make_io(rec, heading);
+  StepIO io = make_io(rec, heading, E);
   io.draws = draws; io.explicit_draws = explicit_draws; io.seed = seed; io.env_id_base = env_id; io.obs = obs;
+  E->seed = seed; E->env_id = env_id;
   run_reset(E->S, E->m, E->c, io, 0, 0);
 }
 void emul_forward(void* h, double* rec, double* heading, double* obs, double* info) {

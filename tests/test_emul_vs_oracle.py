@@ -118,3 +118,39 @@ def test_contact_spill_path(oracle):
         assert stats[0] == mj.nefc // 6 == 19 and stats[4] == 0
         assert np.abs(em.qvel - mj.qvel).max() < 1e-10
         assert np.abs(em.warm - mj.qacc_warmstart).max() <= 1e-9 * np.abs(mj.qacc_warmstart).max()
+
+
+@pytest.mark.parametrize("task", ["straight", "tracking", "aiming", "vel_track"])
+def test_obs_noise_parity(task):
+    """use_obs_noise (tr_env.py:142, 552-644): the CUDA source's noisy observation against the oracle's restatement on
+    the same normal draws; the true observation (info["real_observation"]) and the reward are untouched by the noise."""
+    rng = np.random.default_rng(3)
+    oe = OracleEnv("flat", "tr_env", desired_action=task, use_obs_noise=True)
+    em = E.Emul("flat", env_kind="tr_env", desired_action=task, use_obs_noise=True, reverse=(task == "tracking"))
+    em.set_noise(77, 5)
+    draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
+    o_true, o_em = oe.reset(draws), em.reset(draws, seed=77, env_id=5)
+    assert np.abs(em.real_obs - o_true).max() < 1e-7
+    assert np.abs(oe.noisy_obs(o_true, E.obs_normals(77, 5, 1, 0, 45)) - o_em).max() < 1e-7
+    for st in range(1, 5):
+        a = rng.uniform(-0.45, 0.15, 6)
+        ob1, r1, _, _, _ = oe.step(a)
+        ob2, r2, _, _ = em.step(a)
+        assert np.abs(em.real_obs - ob1).max() < 1e-7 and abs(r1 - r2) <= 1e-7 * max(1.0, abs(r1))
+        assert np.abs(oe.noisy_obs(ob1, E.obs_normals(77, 5, 1, st, 45)) - ob2).max() < 1e-7
+        assert 0.01 < np.abs(ob2[:36] - ob1[:36]).max() < 0.5          # the noise really is there (stdev 0.05)
+
+
+def test_obs_noise_draws_are_standard_normal_and_keyed():
+    z = np.array([E.obs_normals(9, s, 1, 3, 45) for s in range(3000)])
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.06            # the two outputs of a Box-Muller pair
+    a = E.obs_normals(9, 4, 1, 3, 45)
+    assert np.array_equal(a, E.obs_normals(9, 4, 1, 3, 45))
+    for other in (E.obs_normals(10, 4, 1, 3, 45), E.obs_normals(9, 5, 1, 3, 45), E.obs_normals(9, 4, 2, 3, 45), E.obs_normals(9, 4, 1, 4, 45)):
+        assert not np.array_equal(a, other)
+
+
+def test_obs_noise_is_a_tr_env_option():
+    with pytest.raises(ValueError):
+        E.Emul("flat", env_kind="tensegrity_env", use_obs_noise=True)

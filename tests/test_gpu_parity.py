@@ -328,3 +328,64 @@ def test_pretrained_policies_reproduce_reference_training_statistics():
               % (got, ref, speed, s["yaw_sum"] / (s["length_sum"] * v.dt)))
         assert abs(got - ref) < 0.2 * abs(ref) + 0.01, (pol, got, ref)
         v.close()
+
+
+@pytest.mark.gpu
+def test_obs_noise_on_gpu_matches_restatement_and_is_reproducible():
+    """use_obs_noise through the C ABI: obs - real_obs = stdev * z with the Philox normals of (seed, env id, reset
+    count, episode step); tracking vector / yaw re-derived as in tr_env.py:626-639; same seed -> same noise."""
+    import torch
+    from emul import emul as E
+    from oracle.envs import OracleEnv
+    from tensegrity_rl_b200 import TensegrityVecEnv
+    n, seed = 256, 21
+    mk = lambda: TensegrityVecEnv(n, xml_file="flat", env="tr_env", desired_action="tracking", use_obs_noise=True,
+                                  seed=seed, env_id_base=1000, auto_reset=False)
+    v, w = mk(), mk()
+    oe = OracleEnv("flat", "tr_env", desired_action="tracking", use_obs_noise=True)
+    o0, o0w = v.reset_tensor().cpu().numpy(), w.reset_tensor().cpu().numpy()
+    assert np.array_equal(o0, o0w)
+    real0 = v.real_obs.cpu().numpy()
+    for e in (0, 17, 255):
+        z = E.obs_normals(seed, 1000 + e, 1, 0, 45)
+        assert np.abs(oe.noisy_obs(real0[e], z) - o0[e]).max() < 1e-9
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for st in range(1, 4):
+        a = -0.45 + 0.6 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+        ob = v.step_tensor(a)[0].cpu().numpy()
+        obw = w.step_tensor(a)[0].cpu().numpy()
+        assert np.array_equal(ob, obw)
+        real = v.real_obs.cpu().numpy()
+        for e in (0, 17, 255):
+            z = E.obs_normals(seed, 1000 + e, 1, st, 45)
+            assert np.abs(oe.noisy_obs(real[e], z) - ob[e]).max() < 1e-9
+    d = (ob[:, :36] - real[:, :36]) / 0.05
+    assert abs(d.mean()) < 0.03 and abs(d.std() - 1) < 0.03
+    dt = (ob[:, 36:45] - real[:, 36:45]) / 0.02
+    assert abs(dt.std() - 1) < 0.05
+    # the noise-free twin computes the same true observations: noise never feeds back into the dynamics or rewards
+    t = TensegrityVecEnv(n, xml_file="flat", env="tr_env", desired_action="tracking", seed=seed, env_id_base=1000, auto_reset=False)
+    t.reset_tensor()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for st in range(1, 4):
+        a = -0.45 + 0.6 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+        tob, trew, _ = t.step_tensor(a)
+    assert torch.equal(tob, v.real_obs) and torch.equal(trew, v.reward)
+    # SB3-protocol info dict carries the true observation
+    obs_h, rew_h, done_h, infos = v.step(np.full((n, 6), 0.1))
+    assert np.abs(infos[3]["real_observation"] - v.real_obs[3].cpu().numpy()).max() == 0 if infos[3] else True
+    for x in (v, w, t):
+        x.close()
+
+
+@pytest.mark.gpu
+def test_single_env_obs_noise_info():
+    from tensegrity_rl_b200 import envs
+    e = envs.tr_env(xml_file="flat", desired_action="straight", use_obs_noise=True)
+    o, _ = e.reset(seed=4)
+    ob, r, term, trunc, info = e.step(np.full(6, 0.0, np.float32))
+    assert ob.shape == (45,) and info["real_observation"].shape == (45,)
+    d = ob - info["real_observation"]
+    assert 0.005 < np.abs(d).max() < 0.5 and np.abs(d[36:]).max() < 0.15
+    with pytest.raises(NotImplementedError):
+        envs.tr_env(xml_file="flat", use_cap_size_noise=True)
