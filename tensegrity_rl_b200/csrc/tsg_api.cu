@@ -27,16 +27,25 @@ static_assert(HEADING_SLOTS == TSG_HEADING_SLOTS, "heading slots");
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 
-constexpr int TSG_VWARPS = TSG_WARPS * (32 / TSG_VW);  // virtual warps (= envs in flight) per CTA
-constexpr size_t SMEM_TOTAL = SMEM_MODEL + SMEM_CFG + TSG_VWARPS * SMEM_SCRATCH;
+// CTA shapes of the step kernel.  Shape 0 (8 warps x 3 CTAs per SM, 80 registers) has the best throughput when the
+// batch fills the machine many times over (711k vs 648k env-steps/s at 65 536 envs); shape 1 (7 warps x 4 CTAs per SM,
+// 72 registers, 28 resident envs per SM) holds 4144 envs at once on 148 SMs, so a 4096-env batch -- BASELINE
+// configs[1] -- runs as ONE wave instead of two: 554k vs 454k env-steps/s.  tsg_create picks per handle (pick_shape).
+template <int SHAPE> struct Shape;
+template <> struct Shape<0> { static constexpr int WARPS = TSG_WARPS, MIN_CTAS = TSG_MIN_CTAS, VWARPS = WARPS * (32 / TSG_VW); };
+template <> struct Shape<1> { static constexpr int WARPS = 7, MIN_CTAS = 4, VWARPS = WARPS * (32 / TSG_VW); };
+template <int SHAPE> constexpr int vwarps_of() { return Shape<SHAPE>::VWARPS; }  // envs in flight per CTA
+template <int SHAPE> constexpr size_t smem_of() { return SMEM_MODEL + SMEM_CFG + Shape<SHAPE>::VWARPS * SMEM_SCRATCH; }
+constexpr int TSG_VWARPS = vwarps_of<0>();
+constexpr size_t SMEM_TOTAL = smem_of<0>();
 
 // One warp per env, persistent CTAs: the grid is sized to fill the machine once (SMs x resident CTAs) and every
 // warp pulls env indices from a global counter until the batch is done, so envs of different cost (contact
 // count, Newton iterations, resets) balance dynamically and the model constants are staged once per CTA in
 // shared memory (lane-indexed reads of them would serialise in the constant cache).  Warps never synchronise
 // with each other after that.
-template <int MODE>
-__global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(const DevModel* __restrict__ gm,
+template <int MODE, int SHAPE = 0>
+__global__ void __launch_bounds__(Shape<SHAPE>::WARPS * 32, Shape<SHAPE>::MIN_CTAS) tsg_env_kernel(const DevModel* __restrict__ gm,
                                                                   const EnvCfg* __restrict__ gc, StepIO io,
                                                                   Con* __restrict__ spill_base, int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char tsg_smem[];
@@ -54,7 +63,8 @@ __global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(c
   const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(smem + SMEM_MODEL);
   int warp = threadIdx.x / TSG_VW, lane = threadIdx.x % TSG_VW;  // virtual warp / lane
   EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
-  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * TSG_VWARPS + warp) * (MAXC - MAXC_S);
+  constexpr int VWARPS = Shape<SHAPE>::VWARPS;
+  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * VWARPS + warp) * (MAXC - MAXC_S);
   WSYNC();
   // items: the n_envs envs, then (STEP: every launch, RESET of all envs: prewarm) the background reset pool slots
   int n_items = io.n_envs + ((MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? io.n_pool : 0);
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(TSG_WARPS * 32, TSG_MIN_CTAS) tsg_env_kernel(c
 #else
     __shared__ int s_base;
     for (;;) {
-      if (threadIdx.x == 0) s_base = atomicAdd(counter, TSG_VWARPS);
+      if (threadIdx.x == 0) s_base = atomicAdd(counter, VWARPS);
       __syncthreads();
       int e = s_base + warp;
       __syncthreads();
@@ -207,7 +217,7 @@ struct TsgHandle {
   double* d_pool_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
   double* d_realobs_own;
-  int grid[3];
+  int grid[3], grid_step1, shape;   // shape: CTA shape of the step kernel (Shape<>), grid_step1: its grid for shape 1
   cudaStream_t own_stream;
 };
 
@@ -232,27 +242,41 @@ static size_t extra_smem() {
   if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
   return (size_t)v;
 }
-template <int MODE>
-static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
+template <int MODE, int SHAPE>
+static int launch_shape(TsgHandle* h, const StepIO& io, cudaStream_t s, int grid) {
   CK(cudaMemsetAsync(h->d_counter, 0, 2 * sizeof(int), s));
-  tsg_env_kernel<MODE><<<h->grid[MODE], TSG_WARPS * 32, SMEM_TOTAL + extra_smem(), s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
+  tsg_env_kernel<MODE, SHAPE><<<grid, Shape<SHAPE>::WARPS * 32, smem_of<SHAPE>() + extra_smem(), s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
 }
 template <int MODE>
-static int setup_kernel(TsgHandle* h, int num_sms, int* max_grid) {
-  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_TOTAL + extra_smem())));
+static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
+  if (MODE == MODE_STEP && h->shape == 1) return launch_shape<MODE_STEP, 1>(h, io, s, h->grid_step1);
+  return launch_shape<MODE, 0>(h, io, s, h->grid[MODE]);
+}
+template <int MODE, int SHAPE>
+static int setup_kernel(TsgHandle* h, int num_sms, int* grid, int* max_spill_warps) {
+  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_of<SHAPE>() + extra_smem())));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE>, TSG_WARPS * 32, SMEM_TOTAL + extra_smem()));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE, SHAPE>, Shape<SHAPE>::WARPS * 32, smem_of<SHAPE>() + extra_smem()));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
   // The shared-memory carve-out is left to the driver's default (the smallest configuration that holds the resident
   // CTAs): what is not carved out stays L1, which serves the per-thread stack and the contact spill area.  With 2
   // contact slots per env the 3 CTAs fit the 164 KB configuration (92 KB L1) instead of 196 KB: +5 % (profiles/).
-  int need = (h->n_envs + h->n_pool + TSG_VWARPS - 1) / TSG_VWARPS, full = num_sms * per_sm;
-  h->grid[MODE] = need < full ? need : full;
-  if (h->grid[MODE] > *max_grid) *max_grid = h->grid[MODE];
+  constexpr int VW = vwarps_of<SHAPE>();
+  int need = (h->n_envs + h->n_pool + VW - 1) / VW, full = num_sms * per_sm;
+  *grid = need < full ? need : full;
+  if (*grid * VW > *max_spill_warps) *max_spill_warps = *grid * VW;
   return 0;
+}
+// which CTA shape steps this handle's batch faster: waves needed x measured time of one wave (ms, B200, profiles/)
+static int pick_shape(int n_envs, int num_sms) {
+  const char* e = getenv("TSG_SHAPE");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+  auto waves = [&](int warps, int ctas) { int groups = (n_envs + warps - 1) / warps, slots = num_sms * ctas; return (groups + slots - 1) / slots; };
+  double t0 = waves(Shape<0>::WARPS, Shape<0>::MIN_CTAS) * 5.0, t1 = waves(Shape<1>::WARPS, Shape<1>::MIN_CTAS) * 6.4;
+  return t1 < t0 ? 1 : 0;
 }
 
 int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int device, long long env_id_base,
@@ -297,10 +321,12 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
   CK(cudaMemset(h->d_heading, 0, n * HEADING_SLOTS * sizeof(double)));
   CK(cudaMemset(h->d_draws, 0, n * NDRAW * sizeof(double)));
   CK(cudaMemset(h->d_done, 0, n));
-  int max_grid = 0;
-  if (setup_kernel<MODE_STEP>(h, prop.multiProcessorCount, &max_grid) || setup_kernel<MODE_RESET>(h, prop.multiProcessorCount, &max_grid) ||
-      setup_kernel<MODE_FORWARD>(h, prop.multiProcessorCount, &max_grid)) { tsg_destroy(h); return -2; }
-  CK(cudaMalloc(&h->d_spill, (size_t)max_grid * TSG_VWARPS * (MAXC - MAXC_S) * sizeof(Con)));
+  int spill_warps = 0, sms = prop.multiProcessorCount;
+  h->shape = (TSG_VW == 32) ? pick_shape(n_envs, sms) : 0;
+  if (setup_kernel<MODE_STEP, 0>(h, sms, &h->grid[MODE_STEP], &spill_warps) || setup_kernel<MODE_STEP, 1>(h, sms, &h->grid_step1, &spill_warps) ||
+      setup_kernel<MODE_RESET, 0>(h, sms, &h->grid[MODE_RESET], &spill_warps) ||
+      setup_kernel<MODE_FORWARD, 0>(h, sms, &h->grid[MODE_FORWARD], &spill_warps)) { tsg_destroy(h); return -2; }
+  CK(cudaMalloc(&h->d_spill, (size_t)spill_warps * (MAXC - MAXC_S) * sizeof(Con)));
   CK(cudaMalloc(&h->d_counter, 2 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   if (ec.use_obs_noise) {   // the noise-free observation always has a home; tsg_set_real_obs redirects it
@@ -346,11 +372,13 @@ int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
 }
 int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes, int* regs_per_thread) {
   (void)h;
-  if (warps_per_cta) *warps_per_cta = TSG_WARPS * 100 + TSG_VW;  // physical warps per CTA * 100 + lanes per env
-  if (smem_bytes) *smem_bytes = (int)SMEM_TOTAL;
+  int w = h->shape == 1 ? Shape<1>::WARPS : Shape<0>::WARPS;
+  if (warps_per_cta) *warps_per_cta = w * 100 + TSG_VW;  // physical warps per CTA * 100 + lanes per env
+  if (smem_bytes) *smem_bytes = (int)(h->shape == 1 ? smem_of<1>() : smem_of<0>());
   if (regs_per_thread) {
     cudaFuncAttributes a;
-    CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP>));
+    if (h->shape == 1) CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP, 1>));
+    else CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP, 0>));
     *regs_per_thread = a.numRegs;
   }
   return 0;
