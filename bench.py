@@ -158,6 +158,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the JSON line must be the only thing on stdout: NCCL's VERSION/INFO banner goes to stdout too
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
 
@@ -299,7 +302,7 @@ def main():
             out["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     env.close()
     if world > 1:
         dist.destroy_process_group()

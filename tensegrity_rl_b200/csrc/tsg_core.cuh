@@ -781,6 +781,31 @@ TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
     prism[9 + 3 * j] = x; prism[10 + 3 * j] = y; prism[11 + 3 * j] = z;
   }
 }
+// flags the (geom, prism) items [base, base + span) whose prism top reaches the geom's AABB bottom and lists them, in
+// order, in S.u.col.cand (at most MAXCAND entries are stored); returns how many were flagged
+TSG_FN int hf_flag_items(Scratch& S, const DevModel& m, int lane, int base, int span) {
+  constexpr int PMAX = 24;
+  int ncand = 0;
+  LANE_FOR_ALL(ii, span) {   // every lane takes part in the scan
+    int i = base + ii, g = i / PMAX, p = i % PMAX, flag = 0;
+    if (ii < span && g < NGEOM) {
+      int per_row = S.u.col.hf_cell[g][1], nrows = S.u.col.hf_cell[g][3];
+      if (per_row > 0 && p < per_row * nrows) {
+        int r = S.u.col.hf_cell[g][2] + p / per_row, k = p % per_row, cmin = S.u.col.hf_cell[g][0];
+        double zmin = S.u.col.hf_zmin[g];
+        for (int j = 0; j < 3; j++) {
+          int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
+          if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
+        }
+      }
+      if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
+    }
+    int slot = scan_slot(flag, ncand, lane);
+    if (flag && slot < MAXCAND) S.u.col.cand[slot] = i;
+  }
+  WSYNC();
+  return ncand;
+}
 TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) {
   LANE_FOR(g, NGEOM) {
     int b = g / 5;
@@ -818,29 +843,16 @@ TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) 
     S.u.col.hf_zmin[g] = zmin;
   }
   WSYNC();
-  // candidates (geom, prism) in MuJoCo's order, processed in blocks of MAXCAND items so the list cannot overflow
-  constexpr int PMAX = 24;
+  // candidates (geom, prism) in MuJoCo's order.  All NGEOM * PMAX items are flagged first; when the whole list fits
+  // the MAXCAND slots (the usual case: a dozen candidates) it is handed to MPR in ONE go -- one or two lane-parallel
+  // passes per substep instead of one per 64-item block that has a candidate -- else the blocks are processed one at
+  // a time, so the list can never overflow.
+  constexpr int PMAX = 24, NITEM = NGEOM * PMAX;
+  int ntot = hf_flag_items(S, m, lane, 0, NITEM);
+  const bool one = ntot <= MAXCAND;
   TSG_UNROLL1
-  for (int base = 0; base < NGEOM * PMAX; base += MAXCAND) {
-    int ncand = 0;
-    LANE_FOR_ALL(ii, MAXCAND) {
-      int i = base + ii, g = i / PMAX, p = i % PMAX, flag = 0;
-      if (ii < MAXCAND && g < NGEOM) {
-        int per_row = S.u.col.hf_cell[g][1], nrows = S.u.col.hf_cell[g][3];
-        if (per_row > 0 && p < per_row * nrows) {
-          int r = S.u.col.hf_cell[g][2] + p / per_row, k = p % per_row, cmin = S.u.col.hf_cell[g][0];
-          double zmin = S.u.col.hf_zmin[g];
-          for (int j = 0; j < 3; j++) {
-            int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
-            if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
-          }
-        }
-        if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
-      }
-      int slot = scan_slot(flag, ncand, lane);
-      if (flag) S.u.col.cand[slot] = i;
-    }
-    WSYNC();
+  for (int base = 0; base < NITEM; base += (one ? NITEM : MAXCAND)) {
+    int ncand = one ? ntot : hf_flag_items(S, m, lane, base, MAXCAND);
     LANE_FOR_ALL(n, ncand) {
       bool hit = false;
       double depth = 0, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0};
