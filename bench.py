@@ -224,8 +224,12 @@ def main():
         hd = torch.empty(n, dtype=torch.uint8).pin_memory()
         dc = torch.empty(n, 6, dtype=torch.float64, device=dev)
         gen = torch.Generator(); gen.manual_seed(99 + rank)
-        ksteps = max(3, min(args.steps, 10))
-        hsrc = CTRL_LO + (CTRL_HI - CTRL_LO) * torch.rand(ksteps + 2, n, 6, generator=gen, dtype=torch.float64)
+        ksteps, kwarm = args.steps, args.warmup
+        hsrc = CTRL_LO + (CTRL_HI - CTRL_LO) * torch.rand(ksteps + kwarm, n, 6, generator=gen, dtype=torch.float64)
+        # same workload as the device-timed loop: a fresh reset, W warm-up steps, then K timed steps (the cost of a
+        # step drifts with the time since reset -- more contacts and Newton iterations as the tendons contract)
+        env.reset_tensor()
+        torch.cuda.synchronize()
 
         def host_step(k):
             hc.copy_(hsrc[k])                            # the caller's actions land in pinned memory
@@ -233,19 +237,20 @@ def main():
             obs, rew, done = env.step_tensor(dc, want_info=False)
             ho.copy_(obs, non_blocking=True); hr.copy_(rew, non_blocking=True); hd.copy_(done, non_blocking=True)  # D2H
             torch.cuda.synchronize()
-        for k in range(2):
+        for k in range(kwarm):
             host_step(k)
         barrier()
         t0 = time.perf_counter()
         for k in range(ksteps):
-            host_step(2 + k)
+            host_step(kwarm + k)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * ksteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 6 * 8,
                "d2h_bytes_per_step": n * (env.obs_dim * 8 + 8 + 1), "steps": ksteps,
-               "api": "TensegrityVecEnv.step_tensor with pinned host ctrl/obs/reward/done copies"}
+               "warmup": kwarm,
+               "api": "TensegrityVecEnv.step_tensor with pinned host ctrl/obs/reward/done copies, wall clock, no L2 flush"}
 
     sweep = {}
     if rank == 0 and world == 1 and args.sweep:
