@@ -36,8 +36,6 @@ template <> struct Shape<0> { static constexpr int WARPS = TSG_WARPS, MIN_CTAS =
 template <> struct Shape<1> { static constexpr int WARPS = 7, MIN_CTAS = 4, VWARPS = WARPS * (32 / TSG_VW); };
 template <int SHAPE> constexpr int vwarps_of() { return Shape<SHAPE>::VWARPS; }  // envs in flight per CTA
 template <int SHAPE> constexpr size_t smem_of() { return SMEM_MODEL + SMEM_CFG + Shape<SHAPE>::VWARPS * SMEM_SCRATCH; }
-constexpr int TSG_VWARPS = vwarps_of<0>();
-constexpr size_t SMEM_TOTAL = smem_of<0>();
 
 // One warp per env, persistent CTAs: the grid is sized to fill the machine once (SMs x resident CTAs) and every
 // warp pulls env indices from a global counter until the batch is done, so envs of different cost (contact
