@@ -281,6 +281,12 @@ def main():
             pass
         fl = flops_per_env_step(ncon, niter)
         tflops = fl * n / (kernel_ms * 1e-3) / 1e12
+        fp64_peak, fp64_src = 37.0, "nominal"
+        try:   # DFMA peak measured on this pool's B200s with tools/proto/peak_fma.cu
+            fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "r1c_vector_peaks.json")))["fp64_dfma_tflops"]
+            fp64_src = "measured (profiles/r1c_vector_peaks.json)"
+        except Exception:  # noqa: BLE001
+            pass
         cfgk = env.kernel_config()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -300,8 +306,8 @@ def main():
                          "note": "the path is instruction-issue / barrier bound, not HBM bound (SURVEY 8d): HBM axis reported for completeness; "
                                  "traffic (ncu, scaled per env) exceeds the algorithmic bytes because per-thread stack and the "
                                  "contact spill area (> L2) stream through DRAM, at <1% of HBM peak",
-                         "fp64_model": {"flops_per_env_step": fl, "achieved_tflops": tflops, "nominal_peak_tflops": 37.0,
-                                        "frac": tflops / 37.0}},
+                         "fp64_model": {"flops_per_env_step": fl, "achieved_tflops": tflops, "peak_tflops": fp64_peak,
+                                        "peak_source": fp64_src, "frac": tflops / fp64_peak}},
         }
         if e2e:
             out["e2e"] = e2e
