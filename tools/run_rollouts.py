@@ -62,6 +62,11 @@ def gpu_rollout(name, n_envs, steps, deterministic, seed=0, rank=0, world=1, loc
     s = rollout(v, actor, steps, deterministic)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    if world > 1:   # device-timed, max over ranks
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     s["env_steps_per_s"] = world * n_envs * steps / ms * 1e3
     s["ncon"], s["niter_per_substep"] = float(v.info[:, 19].mean()), float(v.info[:, 20].mean()) / 20
     s["overflow"], s["bad"] = float(v.info[:, 28].sum()), float(v.info[:, 29].sum())
@@ -82,6 +87,8 @@ if __name__ == "__main__":
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(lr)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout (one JSON line per config)
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     for name in (CONFIGS if args.config == "all" else args.config.split(",")):
         out = {"config": name, "envs_per_gpu": args.envs, "steps": args.steps, "n_gpus": world,
