@@ -158,10 +158,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the JSON line must be the only thing on stdout: NCCL's VERSION/INFO banner goes to stdout too
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # the JSON line must be the only thing on stdout: NCCL prints its version banner there when NCCL_DEBUG is set
+        # (at communicator creation), so stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n = args.envs
 
     def barrier():

@@ -87,9 +87,12 @@ if __name__ == "__main__":
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(lr)
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout (one JSON line per config)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)   # NCCL's version banner goes to stdout: park it on stderr
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+            dist.barrier(device_ids=[lr]); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     for name in (CONFIGS if args.config == "all" else args.config.split(",")):
         out = {"config": name, "envs_per_gpu": args.envs, "steps": args.steps, "n_gpus": world,
                "policy": CONFIGS[name][3], "stochastic": not args.deterministic}
