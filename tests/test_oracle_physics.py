@@ -183,3 +183,40 @@ def test_heightfield_flat_region_supports_weight(oracle):
     assert mj.qpos[2::7].min() > -1.2  # resting on the terrain, not fallen through
     assert abs(mj.qvel).max() < 0.5
     assert mj.cfrc_ext[0, 5] == pytest.approx(-117.72, rel=0.2)
+
+
+def _rotate_state(q, v, w, phi, shift):
+    """the same physical state seen from a frame rotated by phi about z and shifted in the plane: free-joint positions
+    and linear velocities rotate, quaternions get the z-rotation on the left, body-frame angular velocities are unchanged"""
+    c, s = np.cos(phi), np.sin(phi)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    qz = np.array([np.cos(phi / 2), 0, 0, np.sin(phi / 2)])
+    q2, v2, w2 = q.copy(), v.copy(), w.copy()
+    for b in range(3):
+        q2[7 * b:7 * b + 3] = R @ q[7 * b:7 * b + 3] + np.array([shift[0], shift[1], 0.0])
+        a, bq = qz, q[7 * b + 3:7 * b + 7]
+        q2[7 * b + 3:7 * b + 7] = [a[0] * bq[0] - a[3] * bq[3], a[0] * bq[1] - a[3] * bq[2], a[0] * bq[2] + a[3] * bq[1], a[0] * bq[3] + a[3] * bq[0]]
+        v2[6 * b:6 * b + 3] = R @ v[6 * b:6 * b + 3]
+        w2[6 * b:6 * b + 3] = R @ w[6 * b:6 * b + 3]
+    return q2, v2, w2
+
+
+def test_flat_floor_dynamics_are_equivariant_under_planar_motions(oracle):
+    """Physics pin that needs no MuJoCo binary: on the infinite flat floor the step commutes with rotations about z
+    and translations in the plane (contacts, friction cones, tendons, gravity all respect that symmetry).  Any frame
+    mix-up in contact Jacobians, cone bases, body-frame angular velocities or the quaternion integrator breaks it."""
+    rng = np.random.default_rng(4)
+    a, b = oracle.MjLike("flat"), oracle.MjLike("flat")
+    a.reset_data(); a.ctrl[:] = -0.3
+    worst = 0.0
+    for st in range(40):
+        ctrl = rng.uniform(-0.45, -0.15, 6)
+        phi, shift = rng.uniform(-np.pi, np.pi), rng.uniform(-3, 3, 2)
+        q2, v2, w2 = _rotate_state(a.qpos, a.qvel, a.qacc_warmstart, phi, shift)
+        b.reset_data(); b.qpos[:] = q2; b.qvel[:] = v2; b.qacc_warmstart[:] = w2; b.act[:] = a.act
+        a.ctrl[:] = ctrl; b.ctrl[:] = ctrl
+        a.step(5); b.step(5)
+        qe, ve, _ = _rotate_state(a.qpos, a.qvel, a.qacc_warmstart, phi, shift)
+        worst = max(worst, np.abs(b.qpos - qe).max(), np.abs(b.qvel - ve).max() / max(1.0, np.abs(ve).max()))
+        assert np.abs(b.ten_length - a.ten_length).max() < 1e-9
+    assert worst < 1e-8, worst
