@@ -116,6 +116,7 @@ struct DevModel {
   // floor
   int floor_type, nrow, ncol, pad2;
   double fpos[3], fnormal[3], hsize[4];
+  double hdx, hdy;   // height-field cell size: 2 * hsize[0] / (ncol - 1), 2 * hsize[1] / (nrow - 1)
   const float* hdata;
   double qpos0[NQ];
   unsigned char tri_i[NTRI + 5], tri_j[NTRI + 5];  // packed-triangle index -> (row, col)
@@ -772,7 +773,7 @@ TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
 // floor = height field (hfield frame axis-aligned at fpos): geom AABBs -> prism candidates -> MPR
 TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
   // prism k of row r: vertices n = k, k+1, k+2 of the strip (c = cmin + n/2, i = n%2 -> row r+1 / r)
-  double dx = tsg_div(2.0 * m.hsize[0], (double)(m.ncol - 1)), dy = tsg_div(2.0 * m.hsize[1], (double)(m.nrow - 1));
+  double dx = m.hdx, dy = m.hdy;
   for (int j = 0; j < 3; j++) {
     int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
     double x = dx * c - m.hsize[0], y = dy * rr - m.hsize[1];
@@ -780,6 +781,34 @@ TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
     prism[3 * j] = x; prism[3 * j + 1] = y; prism[3 * j + 2] = -m.hsize[3];
     prism[9 + 3 * j] = x; prism[10 + 3 * j] = y; prism[11 + 3 * j] = z;
   }
+}
+// Conservative cull before MPR: a prism lies entirely on or below the plane through its three top vertices, so a geom
+// whose support point towards that plane is still above it (by more than a rounding slack) cannot touch the prism --
+// MPR would report "no contact" for it (MuJoCo runs MPR on every prism that passes the height test; dropping pairs
+// that cannot collide does not change the contact list).  Sphere: n.c - r|n|; cylinder: n.c - (hl |n.a| + r |n x a|).
+TSG_FN bool hf_above_top_plane(const Scratch& S, const DevModel& m, int g, int r, int cmin, int k) {
+  double top[9], gc[3], pos[3], e1[3], e2[3], n[3];
+  for (int j = 0; j < 3; j++) {   // the three top vertices of hf_prism(m, r, cmin, k)
+    int q = k + j, c = cmin + q / 2, rr = r + ((q & 1) ? 0 : 1);
+    top[3 * j] = m.hdx * c - m.hsize[0]; top[3 * j + 1] = m.hdy * rr - m.hsize[1];
+    top[3 * j + 2] = (double)m.hdata[rr * m.ncol + c] * m.hsize[2];
+  }
+  sub3(e1, top + 3, top); sub3(e2, top + 6, top);
+  cross3(n, e1, e2);
+  if (n[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  double nn = dot3(n, n);
+  if (!(nn > 0)) return false;
+  geom_center(S, m, g, gc);
+  sub3(pos, gc, m.fpos);
+  double rad = m.gsize[g][0], reach;
+  if (m.gtype[g] == GEOM_SPHERE) reach = rad * tsg_sqrt(nn);
+  else {
+    const double* R = S.xmat + 9 * (g / 5);
+    double na = n[0] * R[2] + n[1] * R[5] + n[2] * R[8];
+    reach = m.gsize[g][1] * fabs(na) + rad * tsg_sqrt(fmax(0.0, nn - na * na));
+  }
+  double sep = dot3(n, pos) - reach - dot3(n, top);
+  return sep > 1e-9 * tsg_sqrt(nn);
 }
 // flags the (geom, prism) items [base, base + span) whose prism top reaches the geom's AABB bottom and lists them, in
 // order, in S.u.col.cand (at most MAXCAND entries are stored); returns how many were flagged
@@ -797,6 +826,7 @@ TSG_FN int hf_flag_items(Scratch& S, const DevModel& m, int lane, int base, int 
           int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
           if ((double)m.hdata[rr * m.ncol + c] * m.hsize[2] >= zmin) flag = 1;
         }
+        if (flag && hf_above_top_plane(S, m, g, r, cmin, k)) flag = 0;
       }
       if (per_row > 0 && p == PMAX - 1 && per_row * nrows > PMAX) S.overflow = 1;
     }

@@ -88,6 +88,7 @@ inline std::string make_dev_model(const TsgModel& t, DevModel& m, const float* h
     for (int k = 0; k < 9; k++) if (fabs(t.floor_mat[k] - I[k]) > 1e-12) return "height field frame must be axis aligned";
     m.nrow = t.hf_nrow; m.ncol = t.hf_ncol;
     for (int k = 0; k < 4; k++) m.hsize[k] = t.hf_size[k];
+    m.hdx = 2.0 * m.hsize[0] / (double)(m.ncol - 1); m.hdy = 2.0 * m.hsize[1] / (double)(m.nrow - 1);
     m.hdata = hdata_dev;
     if (!hdata_dev || m.nrow < 2 || m.ncol < 2) return "height field data missing";
   }
