@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(Shape<SHAPE>::WARPS * 32, Shape<SHAPE>::MIN_CT
 #if TSG_ALIGNED
   // aligned work loop over the envs: the envs of one alignment scope (physical warp / CTA) are fetched together and
   // walk through the step in phase; a (virtual) warp without an env at the tail runs the idle barrier protocol.
-  // Pool slots (mostly idle) are left to the unaligned loop.
   if (MODE == MODE_STEP) {
 #ifdef TSG_ALIGN_WARP
     constexpr int GROUP = 32 / TSG_VW;
@@ -87,15 +86,22 @@ __global__ void __launch_bounds__(Shape<SHAPE>::WARPS * 32, Shape<SHAPE>::MIN_CT
       __syncthreads();
       int e = s_base + warp;
       __syncthreads();
-      if (e - warp >= io.n_envs) break;
+      if (e - warp >= n_items) break;
 #endif
       if (lane == 0) S.align = 1;
       WSYNC();
       if (e < io.n_envs) run_step(S, m, c, io, e, lane);
-      else for (int s = 0; s < c.frame_skip; s++) aligned_idle_substep();
+      else {
+        // background reset pool slot: a slot that is warming up runs its one warm-up env step of this launch in
+        // phase with the group (same barrier protocol as an env step); ready slots and the tail idle through it
+        bool warming = false;
+        if (e < n_items) warming = (int)io.state[(size_t)e * STATE_STRIDE + SO_FLAGS] <= c.warmup_steps;
+        if (warming) run_pool(S, m, c, io, e - io.n_envs, false, lane);
+        else for (int s = 0; s < c.frame_skip; s++) aligned_idle_substep();
+      }
     }
-    first = io.n_envs;
-    counter += 1;  // the pool items use the second counter
+    first = n_items;
+    counter += 1;  // (nothing is left for the unaligned loop of a step launch)
   }
 #endif
   if (lane == 0) S.align = 0;

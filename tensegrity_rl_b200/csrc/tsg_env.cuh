@@ -566,6 +566,7 @@ TSG_FN void run_pool(EnvScratch& S, const DevModel& m, const EnvCfg& c, const St
   // only the single warm-up step of a launch follows the aligned barrier protocol (exactly one simulate());
   // the begin / finish parts contain extra forward passes and steps and run unaligned
   int aligned = S.align && !finish_now;
+  WSYNC();
   if (lane == 0) S.align = 0;
   WSYNC();
   if (phase == 0) reset_begin(S, m, c, A, lane); else reset_setpoints(S, c, lane);
