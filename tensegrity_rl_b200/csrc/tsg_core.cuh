@@ -57,8 +57,8 @@ namespace tsg {
 
 constexpr int NBAR = 3, NGEOM = 15, NTEN = 9, NEND = 18, NACT = 6, NQ = 21, NV = 18;
 #ifndef TSG_MAXC_S
-#define TSG_MAXC_S 2  // measured: 2 slots let the 3 resident CTAs fit the 164 KB shared-memory configuration (92 KB of L1
-                      // left for the stack and the spill area): 710k vs 695k env-steps/s with 3 slots (196 KB configuration)
+#define TSG_MAXC_S 3  // 3 slots in 6288 B of scratch per env: the 3 resident CTAs stay within the 164 KB shared-memory
+                      // configuration (92 KB of L1 left for the stack and the spill area; 196 KB costs 5 %)
 #endif
 constexpr int MAXC_S = TSG_MAXC_S;       // contact slots per env in shared memory
 constexpr int MAXC = 32;        // total contact slots per env (slots >= MAXC_S spill to a per-warp global area)
@@ -158,9 +158,9 @@ struct Scratch {
   double xstale[9];
   double xmat[27];
   double sph[18];
-  double tlen[NTEN], tdir[NTEN * 3], tJw[NEND * 3];
-  // velocity / force stage
-  double tfrc[NTEN], tB[NTEN], actdot[NACT];
+  double tlen[NTEN];
+  // velocity / force stage (the tendon directions / Jacobian arms / forces live in the union below: u.ten)
+  double actdot[NACT];
   double fsm[NV], asmooth[NV], fcon[NV];
   // solver vectors
   double qacc[NV], grad[NV], search[NV], rhs[NV], dinv[NV];
@@ -171,6 +171,9 @@ struct Scratch {
     struct { double H[NTRI]; } hes;
     struct { double acc[MAXC][3]; } ls;
     struct { double Dblk[NBAR][21]; double cfrc[4][6]; double obs[64]; } post;
+    // tendon directions, Jacobian arms, forces, damping coefficients: alive from stage_tendon to stage_smooth and,
+    // recomputed after the solve, during stage_damping_blocks -- next to post.Dblk, over cfrc / obs (dead inside a substep)
+    struct { double pad_[NBAR * 21]; double tdir[NTEN * 3], tJw[NEND * 3], tfrc[NTEN], tB[NTEN]; } ten;
   } u;
   Con con[MAXC_S];
   Con* spill;  // global memory, MAXC - MAXC_S slots owned by this warp
@@ -402,11 +405,11 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
       sub3(r, p[e], S.qpos + 7 * b);
       cross3(c, r, dir);
       mulMTV(w[e], S.xmat + 9 * b, c);
-      copy3(S.tJw + 3 * end, w[e]);
+      copy3(S.u.ten.tJw + 3 * end, w[e]);
       double s = e ? 1.0 : -1.0;
       vel += s * (dot3(dir, S.qvel + 6 * b) + dot3(w[e], S.qvel + 6 * b + 3));
     }
-    copy3(S.tdir + 3 * t, dir);
+    copy3(S.u.ten.tdir + 3 * t, dir);
     S.tlen[t] = len;
     double frc = 0, Bt = -m.tdamp[t];
     if (m.tk[t] > 0) {
@@ -429,7 +432,7 @@ TSG_FN void stage_tendon(Scratch& S, const DevModel& m, int lane) {
       frc += f;
       if (m.bias[2] != 0 && ((m.flags & 1u) || !clamped)) Bt += m.bias[2];
     }
-    S.tfrc[t] = frc; S.tB[t] = Bt;
+    S.u.ten.tfrc[t] = frc; S.u.ten.tB[t] = Bt;
   }
   WSYNC();
 }
@@ -442,8 +445,8 @@ TSG_FN void stage_smooth(Scratch& S, const DevModel& m, int lane) {
     for (int n = 0; n < m.nends[b]; n++) {
       int end = m.ends[b][n], t = end >> 1;
       double s = (end & 1) ? 1.0 : -1.0;
-      double Jv = j < 3 ? S.tdir[3 * t + j] : S.tJw[3 * end + j - 3];
-      f += s * S.tfrc[t] * Jv;
+      double Jv = j < 3 ? S.u.ten.tdir[3 * t + j] : S.u.ten.tJw[3 * end + j - 3];
+      f += s * S.u.ten.tfrc[t] * Jv;
     }
     double bias;
     if (j < 3) bias = -m.M[i] * m.grav[j];
@@ -465,9 +468,9 @@ TSG_FN void stage_damping_blocks(Scratch& S, const DevModel& m, int lane) {
     double v = 0;
     for (int n = 0; n < m.nends[b]; n++) {
       int end = m.ends[b][n], t = end >> 1;
-      double Jr = r < 3 ? S.tdir[3 * t + r] : S.tJw[3 * end + r - 3];
-      double Jc = c < 3 ? S.tdir[3 * t + c] : S.tJw[3 * end + c - 3];
-      v += S.tB[t] * Jr * Jc;
+      double Jr = r < 3 ? S.u.ten.tdir[3 * t + r] : S.u.ten.tJw[3 * end + r - 3];
+      double Jc = c < 3 ? S.u.ten.tdir[3 * t + c] : S.u.ten.tJw[3 * end + c - 3];
+      v += S.u.ten.tB[t] * Jr * Jc;
     }
     S.u.post.Dblk[b][tri] = v;
   }
@@ -923,9 +926,10 @@ TSG_FN void collide_bars(Scratch& S, const DevModel& m, int lane, int& nslot) {
   TSG_UNROLL1
   for (int base = 0; base < 75; base += MAXCAND) {
     int ncand = 0;
-    LANE_FOR_ALL(ii, MAXCAND) {
+    const int span = 75 - base < MAXCAND ? 75 - base : MAXCAND;   // the last block holds 11 pairs: one lane pass
+    LANE_FOR_ALL(ii, span) {
       int flag = 0, i = base + ii;
-      if (ii < MAXCAND && i < 75) {
+      if (ii < span) {
         int pr = i / 25, b1 = pr == 2 ? 1 : 0, b2 = pr == 0 ? 1 : 2;
         int g1 = 5 * b1 + (i % 25) / 5, g2 = 5 * b2 + i % 5;
         int t1 = m.gtype[g1], t2 = m.gtype[g2];
@@ -1466,6 +1470,7 @@ TSG_FN void stage_solve(EnvScratch& S, const DevModel& m, const EnvCfg& c, int l
 // ------------------------------------------------------------------ implicitfast + advance
 TSG_FN void stage_integrate(Scratch& S, const DevModel& m, int lane) {
   double h = m.h;
+  stage_tendon(S, m, lane);   // the tendon Jacobians shared their storage with the solver: recompute (same inputs, same values)
   stage_damping_blocks(S, m, lane);
   LANE_FOR(b, NBAR) {
     // (M - h D) x = qfrc_smooth + qfrc_constraint on the bar's 6x6 block, in place in shared memory
