@@ -478,7 +478,10 @@ TSG_FN void stage_damping_blocks(Scratch& S, const DevModel& m, int lane) {
 }
 
 // ------------------------------------------------------------------ MPR (libccd semantics)
-struct CObj { int type; double pos[3]; const double* mat; double size[2]; const double* prism; };
+// type 100 = height-field prism, stored as its three (x, y) columns with the top heights and the common base height:
+// vertex i < 3 is (px[i], py[i], pbase), vertex 3 + i is (px[i], py[i], pz[i])  (10 values instead of an 18-double
+// vertex array behind a pointer: the support function is the hot spot of the height-field path)
+struct CObj { int type; double pos[3]; const double* mat; double size[2]; double px[3], py[3], pz[3], pbase; };
 struct Supp { double v[3], v1[3]; };  // v = v1 - v2 ; v2 recovered as v1 - v
 
 TSG_FN bool ccd_is_zero(double x) { return fabs(x) < CCD_EPS; }
@@ -493,9 +496,14 @@ TSG_FN void ccd_normalize(double* v) { double s = tsg_inv(tsg_sqrt(dot3(v, v)));
 
 TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
   if (o.type == 100) {
-    int best = 0; double bd = dot3(o.prism, dir);
-    for (int i = 1; i < 6; i++) { double dd = dot3(o.prism + 3 * i, dir); if (dd > bd) { bd = dd; best = i; } }
-    copy3(out, o.prism + 3 * best);
+    // first maximum of vertex . dir over the vertices in order (bottom 0..2, top 3..5), as libccd's loop finds it
+    double t[3], bd = 0; int best = 0;
+    for (int j = 0; j < 3; j++) t[j] = o.px[j] * dir[0] + o.py[j] * dir[1];
+    for (int i = 0; i < 6; i++) {
+      double dd = t[i % 3] + (i < 3 ? o.pbase : o.pz[i - 3]) * dir[2];
+      if (i == 0 || dd > bd) { bd = dd; best = i; }
+    }
+    out[0] = o.px[best % 3]; out[1] = o.py[best % 3]; out[2] = best < 3 ? o.pbase : o.pz[best - 3];
     return;
   }
   double ld[3], res[3];
@@ -513,7 +521,7 @@ TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
 TSG_FN void obj_center(const CObj& o, double* c) {
   if (o.type == 100) {
     c[0] = c[1] = c[2] = 0;
-    for (int i = 0; i < 6; i++) { c[0] += o.prism[3 * i]; c[1] += o.prism[3 * i + 1]; c[2] += o.prism[3 * i + 2]; }
+    for (int i = 0; i < 6; i++) { c[0] += o.px[i % 3]; c[1] += o.py[i % 3]; c[2] += i < 3 ? o.pbase : o.pz[i - 3]; }
     c[0] /= 6; c[1] /= 6; c[2] /= 6;
   } else copy3(c, o.pos);
 }
@@ -774,16 +782,15 @@ TSG_FN void collide_plane(Scratch& S, const DevModel& m, int lane, int& nslot) {
 }
 
 // floor = height field (hfield frame axis-aligned at fpos): geom AABBs -> prism candidates -> MPR
-TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, double* prism) {
+TSG_FN void hf_prism(const DevModel& m, int r, int cmin, int k, CObj& o) {
   // prism k of row r: vertices n = k, k+1, k+2 of the strip (c = cmin + n/2, i = n%2 -> row r+1 / r)
   double dx = m.hdx, dy = m.hdy;
   for (int j = 0; j < 3; j++) {
     int n = k + j, c = cmin + n / 2, rr = r + ((n & 1) ? 0 : 1);
-    double x = dx * c - m.hsize[0], y = dy * rr - m.hsize[1];
-    double z = (double)m.hdata[rr * m.ncol + c] * m.hsize[2];
-    prism[3 * j] = x; prism[3 * j + 1] = y; prism[3 * j + 2] = -m.hsize[3];
-    prism[9 + 3 * j] = x; prism[10 + 3 * j] = y; prism[11 + 3 * j] = z;
+    o.px[j] = dx * c - m.hsize[0]; o.py[j] = dy * rr - m.hsize[1];
+    o.pz[j] = (double)m.hdata[rr * m.ncol + c] * m.hsize[2];
   }
+  o.pbase = -m.hsize[3];
 }
 // Conservative cull before MPR: a prism lies entirely on or below the plane through its three top vertices, so a geom
 // whose support point towards that plane is still above it (by more than a rounding slack) cannot touch the prism --
@@ -894,11 +901,11 @@ TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) 
         int i = S.u.col.cand[n], g = i / PMAX, p = i % PMAX;
         b = g / 5;
         int per_row = S.u.col.hf_cell[g][1];
-        double prism[18], gc[3];
-        hf_prism(m, S.u.col.hf_cell[g][2] + p / per_row, S.u.col.hf_cell[g][0], p % per_row, prism);
+        double gc[3];
         CObj o1, o2;
-        o1.type = 100; o1.prism = prism; o1.mat = nullptr;
-        o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b; o2.prism = nullptr;
+        hf_prism(m, S.u.col.hf_cell[g][2] + p / per_row, S.u.col.hf_cell[g][0], p % per_row, o1);
+        o1.type = 100; o1.mat = nullptr;
+        o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b;
         geom_center(S, m, g, gc);
         sub3(o2.pos, gc, m.fpos);
         o2.size[0] = m.gsize[g][0]; o2.size[1] = m.gsize[g][1];
@@ -970,9 +977,9 @@ TSG_FN void collide_bars(Scratch& S, const DevModel& m, int lane, int& nslot) {
           copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
         } else {
           CObj o1, o2;
-          o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; o1.prism = nullptr; copy3(o1.pos, c1);
+          o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; copy3(o1.pos, c1);
           o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
-          o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; o2.prism = nullptr; copy3(o2.pos, c2);
+          o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; copy3(o2.pos, c2);
           o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
           double depth;
           hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
