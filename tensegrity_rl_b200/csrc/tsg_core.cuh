@@ -481,7 +481,23 @@ TSG_FN void stage_damping_blocks(Scratch& S, const DevModel& m, int lane) {
 // type 100 = height-field prism, stored as its three (x, y) columns with the top heights and the common base height:
 // vertex i < 3 is (px[i], py[i], pbase), vertex 3 + i is (px[i], py[i], pz[i])  (10 values instead of an 18-double
 // vertex array behind a pointer: the support function is the hot spot of the height-field path)
-struct CObj { int type; double pos[3]; const double* mat; double size[2]; double px[3], py[3], pz[3], pbase; };
+struct CObj { int type, bar; double pos[3]; double size[2]; double px[3], py[3], pz[3], pbase; };   // bar: whose rotation matrix
+// The narrow phase is compiled once, out of line; its objects name their bar instead of carrying a pointer to the
+// bar's rotation matrix, which the support function then reads straight from the env's shared-memory scratch
+// (a pointer stored in the object would make every matrix access a generic load).
+#if TSG_DEVICE
+#define XM_PARAMS int
+#define XM_ARGS 0
+#define XM_PASS 0
+#define XM_BIND                                                                                              \
+  extern __shared__ __align__(16) unsigned char tsg_smem[];                                                  \
+  const double* xmat_base = reinterpret_cast<const EnvScratch*>(tsg_smem + SMEM_MODEL + SMEM_CFG + (threadIdx.x / TSG_VW) * SMEM_SCRATCH)->xmat;
+#else
+#define XM_PARAMS const double* xmat_base
+#define XM_ARGS S.xmat
+#define XM_PASS xmat_base
+#define XM_BIND
+#endif
 struct Supp { double v[3], v1[3]; };  // v = v1 - v2 ; v2 recovered as v1 - v
 
 TSG_FN bool ccd_is_zero(double x) { return fabs(x) < CCD_EPS; }
@@ -494,7 +510,7 @@ TSG_FN bool ccd_eq(double a_, double b_) {
 TSG_FN bool ccd_vec_is_origin(const double* a) { return ccd_eq(a[0], 0) && ccd_eq(a[1], 0) && ccd_eq(a[2], 0); }
 TSG_FN void ccd_normalize(double* v) { double s = tsg_inv(tsg_sqrt(dot3(v, v))); v[0] *= s; v[1] *= s; v[2] *= s; }
 
-TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
+TSG_FN void obj_support(const CObj& o, const double* dir, double* out, const double* xmat_base) {
   if (o.type == 100) {
     // first maximum of vertex . dir over the vertices in order (bottom 0..2, top 3..5), as libccd's loop finds it
     double t[3], bd = 0; int best = 0;
@@ -507,7 +523,8 @@ TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
     return;
   }
   double ld[3], res[3];
-  mulMTV(ld, o.mat, dir);
+  const double* R = xmat_base + 9 * o.bar;
+  mulMTV(ld, R, dir);
   if (o.type == GEOM_SPHERE) scl3(res, ld, o.size[0]);
   else {
     double tmp = tsg_sqrt(ld[0] * ld[0] + ld[1] * ld[1]);
@@ -515,7 +532,7 @@ TSG_FN void obj_support(const CObj& o, const double* dir, double* out) {
     else res[0] = res[1] = 0;
     res[2] = (ld[2] > 0 ? 1.0 : (ld[2] < 0 ? -1.0 : 0.0)) * o.size[1];
   }
-  mulMV(out, o.mat, res);
+  mulMV(out, R, res);
   add3(out, out, o.pos);
 }
 TSG_FN void obj_center(const CObj& o, double* c) {
@@ -525,10 +542,11 @@ TSG_FN void obj_center(const CObj& o, double* c) {
     c[0] /= 6; c[1] /= 6; c[2] /= 6;
   } else copy3(c, o.pos);
 }
-TSG_FN_NOINLINE void mink_support(const CObj& o1, const CObj& o2, const double* dir, Supp& s) {
+TSG_FN_NOINLINE void mink_support(const CObj& o1, const CObj& o2, const double* dir, Supp& s, XM_PARAMS) {
+  XM_BIND
   double nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
-  obj_support(o1, dir, s.v1);
-  obj_support(o2, nd, v2);
+  obj_support(o1, dir, s.v1, xmat_base);
+  obj_support(o2, nd, v2, xmat_base);
   sub3(s.v, s.v1, v2);
 }
 TSG_FN void portal_dir(const Supp* p, double* dir) {
@@ -581,7 +599,7 @@ TSG_FN double tri_dist2_origin(const double* x0, const double* B, const double* 
 }
 // returns true on penetration; dir points from obj1 to obj2
 TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol, int max_iter,
-                                     double* depth, double* dir_out, double* pos_out) {
+                                     double* depth, double* dir_out, double* pos_out, XM_PARAMS) {
   Supp p[4], v4;
   double dir[3], va[3], vb[3], dot, c2[3];
   // ---- discoverPortal
@@ -589,7 +607,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
   sub3(p[0].v, p[0].v1, c2);
   if (ccd_vec_is_origin(p[0].v)) p[0].v[0] += CCD_EPS * 10.0;
   scl3(dir, p[0].v, -1.0); ccd_normalize(dir);
-  mink_support(o1, o2, dir, p[1]);
+  mink_support(o1, o2, dir, p[1], XM_PASS);
   dot = dot3(p[1].v, dir);
   if (ccd_is_zero(dot) || dot < 0) return false;
   cross3(dir, p[0].v, p[1].v);
@@ -603,7 +621,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
     return true;
   }
   ccd_normalize(dir);
-  mink_support(o1, o2, dir, p[2]);
+  mink_support(o1, o2, dir, p[2], XM_PASS);
   dot = dot3(p[2].v, dir);
   if (ccd_is_zero(dot) || dot < 0) return false;
   sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
@@ -611,7 +629,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
   if (dot3(dir, p[0].v) > 0) { Supp t = p[1]; p[1] = p[2]; p[2] = t; scl3(dir, dir, -1.0); }
   for (;;) {
     bool cont = false;
-    mink_support(o1, o2, dir, p[3]);
+    mink_support(o1, o2, dir, p[3], XM_PASS);
     dot = dot3(p[3].v, dir);
     if (ccd_is_zero(dot) || dot < 0) return false;
     cross3(va, p[1].v, p[3].v); dot = dot3(va, p[0].v);
@@ -629,7 +647,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
     portal_dir(p, dir);
     dot = dot3(dir, p[1].v);
     if (ccd_is_zero(dot) || dot > 0) break;
-    mink_support(o1, o2, dir, v4);
+    mink_support(o1, o2, dir, v4, XM_PASS);
     dot = dot3(v4.v, dir);
     if (!(ccd_is_zero(dot) || dot > 0) || portal_reach_tol(p, v4, dir, tol)) return false;
     expand_portal(p, v4);
@@ -637,7 +655,7 @@ TSG_FN_NOINLINE bool mpr_penetration(const CObj& o1, const CObj& o2, double tol,
   // ---- findPenetr
   for (int it = 0;; it++) {
     portal_dir(p, dir);
-    mink_support(o1, o2, dir, v4);
+    mink_support(o1, o2, dir, v4, XM_PASS);
     if (portal_reach_tol(p, v4, dir, tol) || it > max_iter) {
       double pdir[3];
       *depth = tsg_sqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
@@ -904,12 +922,12 @@ TSG_FN void collide_hfield(Scratch& S, const DevModel& m, int lane, int& nslot) 
         double gc[3];
         CObj o1, o2;
         hf_prism(m, S.u.col.hf_cell[g][2] + p / per_row, S.u.col.hf_cell[g][0], p % per_row, o1);
-        o1.type = 100; o1.mat = nullptr;
-        o2.type = m.gtype[g]; o2.mat = S.xmat + 9 * b;
+        o1.type = 100; o1.bar = 0;
+        o2.type = m.gtype[g]; o2.bar = b;
         geom_center(S, m, g, gc);
         sub3(o2.pos, gc, m.fpos);
         o2.size[0] = m.gsize[g][0]; o2.size[1] = m.gsize[g][1];
-        hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, pos);
+        hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, pos, XM_ARGS);
         if (hit && ccd_vec_is_origin(dir)) hit = false;
         if (hit) {
           add3(pos, pos, m.fpos);
@@ -977,12 +995,12 @@ TSG_FN void collide_bars(Scratch& S, const DevModel& m, int lane, int& nslot) {
           copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
         } else {
           CObj o1, o2;
-          o1.type = m.gtype[g1]; o1.mat = S.xmat + 9 * b1; copy3(o1.pos, c1);
+          o1.type = m.gtype[g1]; o1.bar = b1; copy3(o1.pos, c1);
           o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
-          o2.type = m.gtype[g2]; o2.mat = S.xmat + 9 * b2; copy3(o2.pos, c2);
+          o2.type = m.gtype[g2]; o2.bar = b2; copy3(o2.pos, c2);
           o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
           double depth;
-          hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
+          hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos, XM_ARGS);
           if (hit && ccd_vec_is_origin(nrm)) hit = false;
           dist = -depth;
           if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
