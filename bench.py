@@ -90,7 +90,7 @@ def run_reference(args, rank):
         return
     from oracle import oracle as O
     threads = O.lib().tsgo_max_threads()
-    n_envs = args.ref_envs or 32 * threads
+    n_envs = args.ref_envs or 128 * threads          # ~5-10 s of host work at the default --steps / --warmup
     b = O.Batch("flat", n_envs, seed=0)
     b.step(50, lo=0.15, hi=0.15)           # the reset warm-up (50 env steps), untimed, like the GPU arm's reset
     for _ in range(args.warmup):
