@@ -1,0 +1,208 @@
+// tb_mpr.h -- convex narrow phase with libccd's MPR semantics (what MuJoCo 2.3.7 runs for cylinder-cylinder,
+// sphere-cylinder and height-field-prism pairs; libccd is a third-party dependency of MuJoCo, absent from the
+// reference tree, restated here from its published algorithm).  One pair per lane, run to completion by that lane.
+#pragma once
+#include "tb_math.h"
+#include "tb_model.h"
+
+namespace tb {
+
+// type GEOM_SPHERE / GEOM_CYL: centre pos, rotation R (row-major, body frame -> world), size = (radius, half length).
+// type 100 = height-field prism: its three (x, y) columns with the top heights and the common base height; vertex
+// i < 3 is (px[i], py[i], pbase), vertex 3 + i is (px[i], py[i], pz[i]).
+template <typename real>
+struct CObj { int type; real pos[3]; real R[9]; real size[2]; real px[3], py[3], pz[3], pbase; };
+template <typename real> struct Supp { real v[3], v1[3]; };  // v = v1 - v2 ; v2 recovered as v1 - v
+
+template <typename real> TB_FN bool ccd_is_zero(real x) { return tabs(x) < Lim<real>::EPS; }
+template <typename real> TB_FN bool ccd_eq(real a_, real b_) {
+  real ab = tabs(a_ - b_);
+  if (ab < Lim<real>::EPS) return true;
+  real a = tabs(a_), b = tabs(b_);
+  return (b > a) ? (ab < Lim<real>::EPS * b) : (ab < Lim<real>::EPS * a);
+}
+template <typename real> TB_FN bool ccd_vec_is_origin(const real* a) { return ccd_eq(a[0], real(0)) && ccd_eq(a[1], real(0)) && ccd_eq(a[2], real(0)); }
+template <typename real> TB_FN void ccd_normalize(real* v) { real s = trcp(tsqrt(dot3(v, v))); v[0] *= s; v[1] *= s; v[2] *= s; }
+
+template <typename real> TB_FN void obj_support(const CObj<real>& o, const real* dir, real* out) {
+  if (o.type == 100) {
+    // first maximum of vertex . dir over the vertices in order (bottom 0..2, top 3..5), as libccd's loop finds it
+    real t[3], bd = 0; int best = 0;
+    for (int j = 0; j < 3; j++) t[j] = o.px[j] * dir[0] + o.py[j] * dir[1];
+    for (int i = 0; i < 6; i++) {
+      real dd = t[i % 3] + (i < 3 ? o.pbase : o.pz[i - 3]) * dir[2];
+      if (i == 0 || dd > bd) { bd = dd; best = i; }
+    }
+    out[0] = o.px[best % 3]; out[1] = o.py[best % 3]; out[2] = best < 3 ? o.pbase : o.pz[best - 3];
+    return;
+  }
+  real ld[3], res[3];
+  mulMTV(ld, o.R, dir);
+  if (o.type == GEOM_SPHERE) scl3(res, ld, o.size[0]);
+  else {
+    real tmp = tsqrt(ld[0] * ld[0] + ld[1] * ld[1]);
+    if (tmp > Lim<real>::MINVAL) { real it = o.size[0] / tmp; res[0] = ld[0] * it; res[1] = ld[1] * it; }
+    else res[0] = res[1] = 0;
+    res[2] = (ld[2] > 0 ? real(1) : (ld[2] < 0 ? real(-1) : real(0))) * o.size[1];
+  }
+  mulMV(out, o.R, res);
+  add3(out, out, o.pos);
+}
+template <typename real> TB_FN void obj_center(const CObj<real>& o, real* c) {
+  if (o.type == 100) {
+    c[0] = c[1] = c[2] = 0;
+    for (int i = 0; i < 6; i++) { c[0] += o.px[i % 3]; c[1] += o.py[i % 3]; c[2] += i < 3 ? o.pbase : o.pz[i - 3]; }
+    c[0] /= 6; c[1] /= 6; c[2] /= 6;
+  } else copy3(c, o.pos);
+}
+template <typename real> TB_NOINL void mink_support(const CObj<real>& o1, const CObj<real>& o2, const real* dir, Supp<real>& s) {
+  real nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
+  obj_support(o1, dir, s.v1);
+  obj_support(o2, nd, v2);
+  sub3(s.v, s.v1, v2);
+}
+template <typename real> TB_FN void portal_dir(const Supp<real>* p, real* dir) {
+  real a[3], b[3];
+  sub3(a, p[2].v, p[1].v); sub3(b, p[3].v, p[1].v);
+  cross3(dir, a, b); ccd_normalize(dir);
+}
+template <typename real> TB_FN bool portal_reach_tol(const Supp<real>* p, const Supp<real>& v4, const real* dir, real tol) {
+  real dv4 = dot3(v4.v, dir);
+  real d1 = dv4 - dot3(p[1].v, dir), d2 = dv4 - dot3(p[2].v, dir), d3 = dv4 - dot3(p[3].v, dir);
+  d1 = tmin(d1, d2); d1 = tmin(d1, d3);
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+template <typename real> TB_FN void expand_portal(Supp<real>* p, const Supp<real>& v4) {
+  real v4v0[3];
+  cross3(v4v0, v4.v, p[0].v);
+  if (dot3(p[1].v, v4v0) > 0) { if (dot3(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4; }
+  else { if (dot3(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4; }
+}
+template <typename real> TB_FN real seg_dist2_origin(const real* x0, const real* b, real* wit) {
+  real d[3];
+  sub3(d, b, x0);
+  real t = real(-1) * dot3(x0, d); t /= dot3(d, d);
+  if (t < 0 || ccd_is_zero(t)) copy3(wit, x0);
+  else if (t > 1 || ccd_eq(t, real(1))) copy3(wit, b);
+  else { scl3(wit, d, t); add3(wit, wit, x0); }
+  return dot3(wit, wit);
+}
+template <typename real> TB_FN real tri_dist2_origin(const real* x0, const real* B, const real* C, real* wit) {
+  real d1[3], d2[3];
+  sub3(d1, B, x0); sub3(d2, C, x0);
+  real v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  real s, t, dist, dd = w * v - r * r;
+  if (ccd_is_zero(dd)) s = t = -1;
+  else { s = (q * r - w * p) / dd; t = (-s * r - q) / w; }
+  if ((ccd_is_zero(s) || s > 0) && (ccd_eq(s, real(1)) || s < 1) && (ccd_is_zero(t) || t > 0) &&
+      (ccd_eq(t, real(1)) || t < 1) && (ccd_eq(t + s, real(1)) || t + s < 1)) {
+    scl3(d1, d1, s); scl3(d2, d2, t);
+    copy3(wit, x0); add3(wit, wit, d1); add3(wit, wit, d2);
+    dist = dot3(wit, wit);
+  } else {
+    real w2[3], dist2;
+    dist = seg_dist2_origin(x0, B, wit);
+    dist2 = seg_dist2_origin(x0, C, w2);
+    if (dist2 < dist) { dist = dist2; copy3(wit, w2); }
+    dist2 = seg_dist2_origin(B, C, w2);
+    if (dist2 < dist) { dist = dist2; copy3(wit, w2); }
+  }
+  return dist;
+}
+// returns true on penetration; dir points from obj1 to obj2
+template <typename real>
+TB_NOINL bool mpr_penetration(const CObj<real>& o1, const CObj<real>& o2, real tol, int max_iter,
+                              real* depth, real* dir_out, real* pos_out) {
+  Supp<real> p[4], v4;
+  real dir[3], va[3], vb[3], dot, c2[3];
+  // ---- discoverPortal
+  obj_center(o1, p[0].v1); obj_center(o2, c2);
+  sub3(p[0].v, p[0].v1, c2);
+  if (ccd_vec_is_origin(p[0].v)) p[0].v[0] += Lim<real>::EPS * real(10);
+  scl3(dir, p[0].v, real(-1)); ccd_normalize(dir);
+  mink_support(o1, o2, dir, p[1]);
+  dot = dot3(p[1].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return false;
+  cross3(dir, p[0].v, p[1].v);
+  if (ccd_is_zero(dot3(dir, dir))) {
+    // origin on v1 (touching: depth 0, no direction -> MuJoCo drops it) or on the v0-v1 segment
+    if (ccd_vec_is_origin(p[1].v)) return false;
+    real v2[3];
+    sub3(v2, p[1].v1, p[1].v);
+    add3(pos_out, p[1].v1, v2); scl3(pos_out, pos_out, real(0.5));
+    copy3(dir_out, p[1].v); *depth = tsqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
+    return true;
+  }
+  ccd_normalize(dir);
+  mink_support(o1, o2, dir, p[2]);
+  dot = dot3(p[2].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return false;
+  sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
+  cross3(dir, va, vb); ccd_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) { Supp<real> t = p[1]; p[1] = p[2]; p[2] = t; scl3(dir, dir, real(-1)); }
+  for (;;) {
+    bool cont = false;
+    mink_support(o1, o2, dir, p[3]);
+    dot = dot3(p[3].v, dir);
+    if (ccd_is_zero(dot) || dot < 0) return false;
+    cross3(va, p[1].v, p[3].v); dot = dot3(va, p[0].v);
+    if (dot < 0 && !ccd_is_zero(dot)) { p[2] = p[3]; cont = true; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v); dot = dot3(va, p[0].v);
+      if (dot < 0 && !ccd_is_zero(dot)) { p[1] = p[3]; cont = true; }
+    }
+    if (!cont) break;
+    sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
+    cross3(dir, va, vb); ccd_normalize(dir);
+  }
+  // ---- refinePortal
+  for (;;) {
+    portal_dir(p, dir);
+    dot = dot3(dir, p[1].v);
+    if (ccd_is_zero(dot) || dot > 0) break;
+    mink_support(o1, o2, dir, v4);
+    dot = dot3(v4.v, dir);
+    if (!(ccd_is_zero(dot) || dot > 0) || portal_reach_tol(p, v4, dir, tol)) return false;
+    expand_portal(p, v4);
+  }
+  // ---- findPenetr
+  for (int it = 0;; it++) {
+    portal_dir(p, dir);
+    mink_support(o1, o2, dir, v4);
+    if (portal_reach_tol(p, v4, dir, tol) || it > max_iter) {
+      real pdir[3];
+      *depth = tsqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
+      if (ccd_is_zero(pdir[0]) && ccd_is_zero(pdir[1]) && ccd_is_zero(pdir[2])) copy3(pdir, dir);
+      ccd_normalize(pdir);
+      copy3(dir_out, pdir);
+      // findPos: barycentric blend of the witness points
+      real vec[3], b[4], sum;
+      portal_dir(p, dir);
+      cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
+      cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
+      cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
+      cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
+      sum = b[0] + b[1] + b[2] + b[3];
+      if (ccd_is_zero(sum) || sum < 0) {
+        b[0] = 0;
+        cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
+        cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
+        cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
+        sum = b[1] + b[2] + b[3];
+      }
+      real inv = trcp(sum), p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+      // v0's second witness is obj2's centre
+      for (int i = 0; i < 4; i++) {
+        real v2[3];
+        if (i == 0) copy3(v2, c2); else sub3(v2, p[i].v1, p[i].v);
+        addscl3(p1, p[i].v1, b[i]); addscl3(p2, v2, b[i]);
+      }
+      scl3(p1, p1, inv); scl3(p2, p2, inv);
+      add3(pos_out, p1, p2); scl3(pos_out, pos_out, real(0.5));
+      return true;
+    }
+    expand_portal(p, v4);
+  }
+}
+
+}  // namespace tb
