@@ -40,6 +40,8 @@ typedef struct TsgHandle TsgHandle;
 #define TSG_INFO_DIM 32
 #define TSG_CTRL_F64 0
 #define TSG_CTRL_F32 1
+#define TSG_PRECISION_F64 0 /* the reference's arithmetic (MuJoCo is float64); the default */
+#define TSG_PRECISION_F32 1 /* optional fp32 physics (state records, rewards and observations stay f64) */
 
 /* info row layout (doubles) */
 #define TSG_INFO_REW_FWD 0
@@ -78,6 +80,10 @@ int tsg_create(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int d
  * Done envs that find no ready slot fall back to the synchronous reset.  tsg_reset(mask = NULL) prewarms all slots. */
 int tsg_create_pooled(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int n_pool, int device,
                       long long env_id_base, TsgHandle **out);
+/* same, choosing the arithmetic of the physics kernels (TSG_PRECISION_*) */
+int tsg_create_opts(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int n_pool, int device,
+                    long long env_id_base, int precision, TsgHandle **out);
+int tsg_precision(const TsgHandle *h);
 /* counts3 = {done envs, ready slots, slots handed out} of the last auto-reset (synchronous read) */
 int tsg_pool_stats_host(TsgHandle *h, int *counts3);
 int tsg_destroy(TsgHandle *h);
@@ -116,6 +122,10 @@ int tsg_get_real_obs_host(TsgHandle *h, double *real_obs);
 /* mj_forward on the stored states: refreshes the kinematics-derived bookkeeping, optional obs/info */
 int tsg_forward(TsgHandle *h, double *obs_dev, double *info_dev, void *stream);
 
+/* same from host code (MujocoEnv.set_state of a single env): runs on the handle's own stream -- ordered with
+ * tsg_step_host / tsg_reset_host -- and returns after the optional HOST obs / info rows are written */
+int tsg_forward_host(TsgHandle *h, double *obs, double *info);
+
 /* raw state access (HOST buffers, synchronous): any pointer may be NULL */
 int tsg_get_state_host(TsgHandle *h, double *qpos, double *qvel, double *act, double *qacc_warmstart, double *ctrl);
 int tsg_set_state_host(TsgHandle *h, const double *qpos, const double *qvel, const double *act,
@@ -123,6 +133,10 @@ int tsg_set_state_host(TsgHandle *h, const double *qpos, const double *qvel, con
 /* whole records [n_envs][TSG_STATE_STRIDE] (checkpoint / restore of env state), HOST buffers */
 int tsg_get_records_host(TsgHandle *h, double *records);
 int tsg_set_records_host(TsgHandle *h, const double *records);
+/* the heading rings [n_envs][TSG_HEADING_SLOTS] that the records' cursors index (turn / aiming reward delay):
+ * a checkpoint of env state is records + heading rings */
+int tsg_get_heading_host(TsgHandle *h, double *heading);
+int tsg_set_heading_host(TsgHandle *h, const double *heading);
 /* last reset draws [n_envs][TSG_NDRAW], HOST buffer */
 int tsg_get_draws_host(TsgHandle *h, double *draws);
 

@@ -6,7 +6,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = os.path.join(PKG, "csrc", "tsg_api.cu")
-DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("tsg_core.cuh", "tsg_env.cuh", "tsg_host.h")] + [
+DEPS = [SRC] + [os.path.join(PKG, "csrc", f) for f in ("tb_simt.h", "tb_model.h", "tb_math.h", "tb_mpr.h", "tb_core.cuh", "tb_env.cuh")] + [
     os.path.join(ROOT, "include", f) for f in ("tsg.h", "tsg_model.h")]
 SO = os.path.join(PKG, "libtsg.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

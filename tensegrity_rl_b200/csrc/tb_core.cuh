@@ -20,8 +20,9 @@ namespace tb {
 
 constexpr int G = 3;        // lanes per env
 constexpr int EPW = 10;     // envs per warp (lanes 30, 31 idle)
-constexpr int MAXCL = 8;    // contacts one lane can own
-constexpr int KHAND = 3;    // bar-bar contacts per bar pair handed to the env's lane 2
+constexpr int MAXCL = 16;   // contacts one lane can own (a bar lying flat on the floor: 14; local memory, cached as used)
+constexpr int KHAND = 3;    // bar-bar contacts per bar pair handed to the env's lane 2 per round
+constexpr int MAXH = 12;    // bar-bar contacts one pair can have
 constexpr int ZONE_TOP = 0, ZONE_BOTTOM = 1, ZONE_MIDDLE = 2;
 
 template <typename real>
@@ -247,6 +248,112 @@ template <typename real> TB_FN void side_hessian(const Con<real>& c, const Model
   }
 }
 
+// ---- 6x6 block kernels of the Newton solve (packed lower triangles: entry (i, k) at i (i + 1) / 2 + k; full blocks
+// row-major).  Everything is unrolled over static indices, so blocks that are plain local variables stay in registers.
+// A = L D L^T in place: strict lower part = unit L, diagonal = d; dinv = 1 / d
+template <typename real> TB_FN void blk_ldl(real* A, real* dinv) {
+  TB_UNROLL
+  for (int j = 0; j < 6; j++) {
+    real s = A[j * (j + 1) / 2 + j];
+    TB_UNROLL
+    for (int k = 0; k < j; k++) {
+      real t = A[j * (j + 1) / 2 + k];
+      TB_UNROLL
+      for (int q = 0; q < k; q++) t -= A[j * (j + 1) / 2 + q] * A[q * (q + 1) / 2 + q] * A[k * (k + 1) / 2 + q];
+      real l = t * dinv[k];
+      A[j * (j + 1) / 2 + k] = l;
+      s -= l * t;
+    }
+    s = tmax(s, Lim<real>::MINVAL);
+    A[j * (j + 1) / 2 + j] = s;
+    dinv[j] = trcp(s);
+  }
+}
+template <typename real> TB_FN void blk_fwd(const real* L, real* x) {   // x <- L^-1 x
+  TB_UNROLL
+  for (int i = 1; i < 6; i++) {
+    real t = x[i];
+    TB_UNROLL
+    for (int k = 0; k < i; k++) t -= L[i * (i + 1) / 2 + k] * x[k];
+    x[i] = t;
+  }
+}
+template <typename real> TB_FN void blk_bwd(const real* L, real* x) {   // x <- L^-T x
+  TB_UNROLL
+  for (int i = 4; i >= 0; i--) {
+    real t = x[i];
+    TB_UNROLL
+    for (int k = i + 1; k < 6; k++) t -= L[k * (k + 1) / 2 + i] * x[k];
+    x[i] = t;
+  }
+}
+// X <- X L^-T D^-1   (X a full 6x6 block below the diagonal block L D L^T)
+template <typename real> TB_FN void blk_trsm(real* X, const real* L, const real* dinv) {
+  TB_UNROLL
+  for (int r = 0; r < 6; r++) {
+    real u[6];
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) {
+      real t = X[6 * r + k];
+      TB_UNROLL
+      for (int q = 0; q < k; q++) t -= u[q] * L[k * (k + 1) / 2 + q];
+      u[k] = t;
+    }
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) X[6 * r + k] = u[k] * dinv[k];
+  }
+}
+// C (packed) -= A diag(d) A^T
+template <typename real> TB_FN void blk_syrk(real* C, const real* A, const real* Ld) {
+  TB_UNROLL
+  for (int i = 0; i < 6; i++) {
+    real ad[6];
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) ad[k] = A[6 * i + k] * Ld[k * (k + 1) / 2 + k];
+    TB_UNROLL
+    for (int j = 0; j <= i; j++) {
+      real sacc = 0;
+      TB_UNROLL
+      for (int k = 0; k < 6; k++) sacc += ad[k] * A[6 * j + k];
+      C[i * (i + 1) / 2 + j] -= sacc;
+    }
+  }
+}
+// C (full) -= A diag(d) B^T
+template <typename real> TB_FN void blk_gemm(real* C, const real* A, const real* Ld, const real* B) {
+  TB_UNROLL
+  for (int i = 0; i < 6; i++) {
+    real ad[6];
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) ad[k] = A[6 * i + k] * Ld[k * (k + 1) / 2 + k];
+    TB_UNROLL
+    for (int j = 0; j < 6; j++) {
+      real sacc = 0;
+      TB_UNROLL
+      for (int k = 0; k < 6; k++) sacc += ad[k] * B[6 * j + k];
+      C[6 * i + j] -= sacc;
+    }
+  }
+}
+template <typename real> TB_FN void blk_gemv_sub(real* y, const real* A, const real* x) {   // y -= A x
+  TB_UNROLL
+  for (int i = 0; i < 6; i++) {
+    real t = y[i];
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) t -= A[6 * i + k] * x[k];
+    y[i] = t;
+  }
+}
+template <typename real> TB_FN void blk_gemvT_sub(real* y, const real* A, const real* x) {   // y -= A^T x
+  TB_UNROLL
+  for (int i = 0; i < 6; i++) {
+    real t = y[i];
+    TB_UNROLL
+    for (int k = 0; k < 6; k++) t -= A[6 * k + i] * x[k];
+    y[i] = t;
+  }
+}
+
 // ------------------------------------------------------------------ collision pieces
 template <typename real>
 TB_NOINL void plane_cylinder_points(const ModelT<real>& m, const real* pos2, const real* axis_in, real radius, real half,
@@ -458,7 +565,8 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   wsync();   // the tendon end points are dead: the union now carries the bar-bar hand-off
   // ---------------- collision
   if (pass_on) ncon = 0;
-  int overflow = 0, nmpr = 0;
+  int overflow = 0, nmpr = 0, nh = 0;
+  HandCon<real> found[MAXH];   // bar-bar contacts of this lane's pair
   if (pass_on) {
     if (m.floor_type == 0) {
       TB_UNROLL1
@@ -547,7 +655,6 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     // capsule bound (conservative: MPR reports penetration only for intersecting shapes), then sphere-sphere / MPR
     {
       const int p = b, pb1 = p == 2 ? 1 : 0, pb2 = p == 0 ? 1 : 2;
-      int nh = 0;
       const real *X1 = S.xpos + 3 * pb1, *X2 = S.xpos + 3 * pb2, *R1 = S.xmat + 9 * pb1, *R2 = S.xmat + 9 * pb2;
       // bar-level cull: the bars' bounding capsules (axis segment of the whole bar, largest radius)
       TB_UNROLL1
@@ -601,24 +708,35 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
           }
         }
         if (hit && dist < 0) {
-          if (nh < KHAND) {
-            HandCon<real>& hc = S.u.hand[p][nh++];
+          if (nh < MAXH) {
+            HandCon<real>& hc = found[nh++];
             hc.dist = dist; copy3(hc.pos, pos); copy3(hc.nrm, nrm); hc.b1 = cb1; hc.b2 = cb2;
           } else overflow = 1;
         }
       }
-      S.nhand[p] = nh;
     }
   }
-  wsync();
+  // hand-off to lane 2, KHAND contacts per pair and round (one round unless a pair has more than KHAND contacts)
   bool coupled = false;   // does this env have a bar-bar contact (lane 2 owns them)
-  if (pass_on && b == 2) {
-    for (int p = 0; p < 3; p++)
-      for (int k = 0; k < S.nhand[p]; k++) {
-        const HandCon<real>& hc = S.u.hand[p][k];
-        add_contact(con, ncon, overflow, hc.b1, hc.b2, hc.dist, hc.pos, hc.nrm, S.xpos);
-        coupled = true;
-      }
+  TB_UNROLL1
+  for (int round = 0;; round++) {
+    const int lo = round * KHAND;
+    if (pass_on) {
+      int cnt = nh - lo; cnt = cnt < 0 ? 0 : (cnt > KHAND ? KHAND : cnt);
+      for (int k = 0; k < cnt; k++) S.u.hand[b][k] = found[lo + k];
+      S.nhand[b] = cnt;
+    }
+    wsync();
+    if (pass_on && b == 2) {
+      for (int p = 0; p < 3; p++)
+        for (int k = 0; k < S.nhand[p]; k++) {
+          const HandCon<real>& hc = S.u.hand[p][k];
+          add_contact(con, ncon, overflow, hc.b1, hc.b2, hc.dist, hc.pos, hc.nrm, S.xpos);
+          coupled = true;
+        }
+    }
+    if (!any(pass_on && nh > lo + KHAND)) break;
+    wsync();
   }
   coupled = grp_any(coupled, base);
   {
@@ -755,14 +873,13 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       }
       wsync();
       if (go && coupled && b == 2) {
-        real Hd[NV * (NV + 1) / 2];
-        for (int e = 0; e < NV * (NV + 1) / 2; e++) Hd[e] = 0;
-        for (int bb = 0; bb < 3; bb++)
-          for (int i = 0, e = 0; i < 6; i++)
-            for (int k = 0; k <= i; k++, e++) {
-              int gi = 6 * bb + i, gk = 6 * bb + k;
-              Hd[gi * (gi + 1) / 2 + gk] = bb < 2 ? S.u.sol.Hg[21 * bb + e] : H[e];
-            }
+        // blocks: D[bar] (packed, 21 each), then O[pair] (full 6x6: rows = the higher bar, cols = the lower one) for the
+        // pairs (1,0), (2,0), (2,1)
+        real Hb[3 * 21 + 3 * 36];
+        real* const Dg = Hb; real* const Og = Hb + 63;
+        bool cpl[3] = {false, false, false};
+        for (int e = 0; e < 42; e++) Dg[e] = S.u.sol.Hg[e];
+        for (int e = 0; e < 21; e++) Dg[42 + e] = H[e];
         TB_UNROLL1
         for (int n = 0; n < ncon; n++) {
           const Con<real>& c = con[n];
@@ -770,102 +887,65 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
           SideJ<real> J1, J2;
           side_rows(c, real(-1), c.r1, S.xmat + 9 * c.b1, J1);
           side_rows(c, real(1), c.r2, S.xmat + 9 * c.b2, J2);
-          real H1[21], H2[21], X[36];   // X: rows = dofs of b2, cols = dofs of b1
-          for (int e = 0; e < 21; e++) H1[e] = H2[e] = 0;
-          for (int e = 0; e < 36; e++) X[e] = 0;
-          side_hessian(c, m, J1, H1);
-          side_hessian(c, m, J2, H2);
+          const int hi = c.b1 > c.b2 ? c.b1 : c.b2, lo = c.b1 > c.b2 ? c.b2 : c.b1, p = hi == 1 ? 0 : (lo == 0 ? 1 : 2);
+          real* X = Og + 36 * p;
+          if (!cpl[p]) { for (int e = 0; e < 36; e++) X[e] = 0; cpl[p] = true; }
+          side_hessian(c, m, J1, Dg + 21 * c.b1);
+          side_hessian(c, m, J2, Dg + 21 * c.b2);
+          const SideJ<real>& Jh = c.b2 > c.b1 ? J2 : J1;   // rows: the higher bar
+          const SideJ<real>& Jl = c.b2 > c.b1 ? J1 : J2;
           const real* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
           for (int r = 0; r < 6; r++) {
             real w = c.wcoef * wt[r];
-            if (w != 0) { real j1[6], j2[6]; side_row6(J1, r, j1); side_row6(J2, r, j2); rank1_gen(X, w, j2, j1); }
+            if (w != 0) { real jh[6], jl[6]; side_row6(Jh, r, jh); side_row6(Jl, r, jl); rank1_gen(X, w, jh, jl); }
           }
           if (c.zone == ZONE_MIDDLE) {
-            real a1[6], b1v[6], a2[6], b2v[6];
-            side_cone(c, m, J1, a1, b1v); side_cone(c, m, J2, a2, b2v);
-            rank1_gen(X, c.ca, a2, a1);
-            rank1_gen(X, -c.cb, b2v, b1v);
-          }
-          for (int i = 0, e = 0; i < 6; i++)
-            for (int k = 0; k <= i; k++, e++) {
-              int g1 = 6 * c.b1 + i, g1k = 6 * c.b1 + k, g2 = 6 * c.b2 + i, g2k = 6 * c.b2 + k;
-              Hd[g1 * (g1 + 1) / 2 + g1k] += H1[e];
-              Hd[g2 * (g2 + 1) / 2 + g2k] += H2[e];
-            }
-          for (int i = 0; i < 6; i++)
-            for (int k = 0; k < 6; k++) {
-              int gi = 6 * c.b2 + i, gk = 6 * c.b1 + k;
-              int hi = gi > gk ? gi : gk, lo = gi > gk ? gk : gi;
-              Hd[hi * (hi + 1) / 2 + lo] += X[6 * i + k];
-            }
-        }
-        // LDL^T, right-looking, zeros skipped; the right-hand side rides along
-        real rhs[NV], dinv[NV];
-        for (int i = 0; i < NV; i++) rhs[i] = S.u.sol.fx[i];
-        TB_UNROLL1
-        for (int k = 0; k < NV; k++) {
-          real dk = tmax(Hd[k * (k + 1) / 2 + k], MINV), inv = trcp(dk);
-          dinv[k] = inv;
-          real yk = rhs[k];
-          TB_UNROLL1
-          for (int i = k + 1; i < NV; i++) {
-            real* Hi = Hd + i * (i + 1) / 2;
-            real t = Hi[k];
-            if (t != 0) {
-              real lik = t * inv;
-              TB_UNROLL1
-              for (int j = k + 1; j <= i; j++) Hi[j] -= lik * Hd[j * (j + 1) / 2 + k];
-              rhs[i] -= lik * yk;
-            }
+            real ah[6], bh[6], al[6], bl[6];
+            side_cone(c, m, Jh, ah, bh); side_cone(c, m, Jl, al, bl);
+            rank1_gen(X, c.ca, ah, al);
+            rank1_gen(X, -c.cb, bh, bl);
           }
         }
-        for (int i = 0; i < NV; i++) rhs[i] *= dinv[i];
-        TB_UNROLL1
-        for (int k = NV - 1; k > 0; k--) {
-          real xk = rhs[k];
-          TB_UNROLL1
-          for (int i = 0; i < k; i++) { real t = Hd[k * (k + 1) / 2 + i]; if (t != 0) rhs[i] -= t * dinv[i] * xk; }
+        // block LDL^T in the order 0, 1, 2; structurally absent blocks are skipped (fill-in only in pair (2,1))
+        real dinv[NV], x[NV];
+        for (int i = 0; i < NV; i++) x[i] = S.u.sol.fx[i];
+        real *D0 = Dg, *D1 = Dg + 21, *D2 = Dg + 42, *O10 = Og, *O20 = Og + 36, *O21 = Og + 72;
+        blk_ldl(D0, dinv);
+        if (cpl[0]) { blk_trsm(O10, D0, dinv); blk_syrk(D1, O10, D0); }
+        if (cpl[1]) { blk_trsm(O20, D0, dinv); blk_syrk(D2, O20, D0); }
+        if (cpl[0] && cpl[1]) {
+          if (!cpl[2]) { for (int e = 0; e < 36; e++) O21[e] = 0; cpl[2] = true; }
+          blk_gemm(O21, O20, D0, O10);
         }
-        for (int i = 0; i < NV; i++) S.u.sol.xv[i] = -rhs[i];
+        blk_ldl(D1, dinv + 6);
+        if (cpl[2]) { blk_trsm(O21, D1, dinv + 6); blk_syrk(D2, O21, D1); }
+        blk_ldl(D2, dinv + 12);
+        blk_fwd(D0, x);
+        if (cpl[0]) blk_gemv_sub(x + 6, O10, x);
+        blk_fwd(D1, x + 6);
+        if (cpl[1]) blk_gemv_sub(x + 12, O20, x);
+        if (cpl[2]) blk_gemv_sub(x + 12, O21, x + 6);
+        blk_fwd(D2, x + 12);
+        for (int i = 0; i < NV; i++) x[i] *= dinv[i];
+        blk_bwd(D2, x + 12);
+        if (cpl[2]) blk_gemvT_sub(x + 6, O21, x + 12);
+        blk_bwd(D1, x + 6);
+        if (cpl[0]) blk_gemvT_sub(x, O10, x + 6);
+        if (cpl[1]) blk_gemvT_sub(x, O20, x + 12);
+        blk_bwd(D0, x);
+        for (int i = 0; i < NV; i++) S.u.sol.xv[i] = -x[i];
       }
       wsync();
       if (go && coupled) for (int k = 0; k < 6; k++) search[k] = S.u.sol.xv[6 * b + k];
       wsync();
     }
-    if (go && !coupled) {
-      // this bar's own 6x6 block: LDL^T and solve in registers
-      real d[6], x[6];
-      TB_UNROLL
-      for (int j = 0; j < 6; j++) {
-        // row j of L (scaled entries t_jk = l_jk d_k are turned into l_jk as they are finished)
-        real s = H[j * (j + 1) / 2 + j];
-        TB_UNROLL
-        for (int k = 0; k < j; k++) {
-          real t = H[j * (j + 1) / 2 + k];
-          TB_UNROLL
-          for (int q = 0; q < k; q++) t -= H[j * (j + 1) / 2 + q] * d[q] * H[k * (k + 1) / 2 + q];
-          real l = t * trcp(d[k]);
-          H[j * (j + 1) / 2 + k] = l;
-          s -= l * t;
-        }
-        d[j] = tmax(s, MINV);
-      }
-      TB_UNROLL
-      for (int i = 0; i < 6; i++) {
-        real t = grad[i];
-        TB_UNROLL
-        for (int k = 0; k < i; k++) t -= H[i * (i + 1) / 2 + k] * x[k];
-        x[i] = t;
-      }
-      TB_UNROLL
-      for (int i = 0; i < 6; i++) x[i] *= trcp(d[i]);
-      TB_UNROLL
-      for (int i = 5; i >= 0; i--) {
-        real t = x[i];
-        TB_UNROLL
-        for (int k = i + 1; k < 6; k++) t -= H[k * (k + 1) / 2 + i] * x[k];
-        x[i] = t;
-      }
+    if (go && !coupled) {   // this bar's own 6x6 block: LDL^T and solve in registers
+      real dinv[6], x[6];
+      for (int k = 0; k < 6; k++) x[k] = grad[k];
+      blk_ldl(H, dinv);
+      blk_fwd(H, x);
+      for (int k = 0; k < 6; k++) x[k] *= dinv[k];
+      blk_bwd(H, x);
       for (int k = 0; k < 6; k++) search[k] = -x[k];
     }
     // ---- exact line search along search: mj_solPrimal's bracketing search as a per-env state machine.  Every tick

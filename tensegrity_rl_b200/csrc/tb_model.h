@@ -87,7 +87,6 @@ struct EnvCfg {
 
 constexpr double MINVAL_D = 1e-15, MAXVAL_D = 1e10, MINIMP_D = 0.0001, MAXIMP_D = 0.9999;
 
-#ifndef __CUDA_ARCH__
 // returns "" on success, else an error message
 template <typename real>
 inline std::string make_model(const TsgModel& t, ModelT<real>& m, const float* hdata_dev) {
@@ -205,6 +204,5 @@ inline std::string make_env_cfg(const TsgEnvConfig& t, const TsgModel& mod, EnvC
   for (int p = 0; p < TSG_NPOSE; p++) for (int k = 0; k < NQ; k++) c.reset_pose[p][k] = t.reset_pose[p][k];
   return "";
 }
-#endif
 
 }  // namespace tb

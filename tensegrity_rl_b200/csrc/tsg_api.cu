@@ -7,18 +7,17 @@
 #include <vector>
 
 #include "../../include/tsg.h"
-#include "tsg_host.h"
+#include "tb_env.cuh"
 
-using namespace tsg;
+using namespace tb;
 
-// Production configuration (profiles/): full warps per env, 8 warps per CTA, 3 CTAs per SM (24 warps, <= 85 registers,
-// 2 contact slots per env in shared memory), the
-// warps of a CTA aligned at substep / Newton-iteration granularity (TSG_ALIGN, default set in tsg_core.cuh).
-#ifndef TSG_MIN_CTAS
-#define TSG_MIN_CTAS 3  // register cap via __launch_bounds__: 65536 / (TSG_MIN_CTAS * TSG_WARPS * 32) registers per thread
+// Production configuration (profiles/): three lanes per env, ten envs per warp, TB_WARPS warps per CTA and
+// TB_MIN_CTAS CTAs per SM (the register cap follows: 65536 / (TB_MIN_CTAS * TB_WARPS * 32) per thread).
+#ifndef TB_MIN_CTAS
+#define TB_MIN_CTAS 2
 #endif
-#ifndef TSG_WARPS
-#define TSG_WARPS 8  // warps (= envs in flight) per CTA; shared memory per CTA = constants + TSG_WARPS * sizeof(EnvScratch)
+#ifndef TB_WARPS
+#define TB_WARPS 5
 #endif
 
 static_assert(STATE_STRIDE == TSG_STATE_STRIDE && INFO_DIM == TSG_INFO_DIM && NDRAW == TSG_NDRAW, "ABI constants");
@@ -27,96 +26,46 @@ static_assert(HEADING_SLOTS == TSG_HEADING_SLOTS, "heading slots");
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 
-// CTA shapes of the step kernel.  Shape 0 (8 warps x 3 CTAs per SM, 80 registers) has the best throughput when the
-// batch fills the machine many times over (711k vs 648k env-steps/s at 65 536 envs); shape 1 (7 warps x 4 CTAs per SM,
-// 72 registers, 28 resident envs per SM) holds 4144 envs at once on 148 SMs, so a 4096-env batch -- BASELINE
-// configs[1] -- runs as ONE wave instead of two: 554k vs 454k env-steps/s.  tsg_create picks per handle (pick_shape).
-template <int SHAPE> struct Shape;
-template <> struct Shape<0> { static constexpr int WARPS = TSG_WARPS, MIN_CTAS = TSG_MIN_CTAS, VWARPS = WARPS * (32 / TSG_VW); };
-template <> struct Shape<1> { static constexpr int WARPS = 7, MIN_CTAS = 4, VWARPS = WARPS * (32 / TSG_VW); };
-template <int SHAPE> constexpr int vwarps_of() { return Shape<SHAPE>::VWARPS; }  // envs in flight per CTA
-template <int SHAPE> constexpr size_t smem_of() { return SMEM_MODEL + SMEM_CFG + Shape<SHAPE>::VWARPS * SMEM_SCRATCH; }
+__host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+template <typename real> __host__ __device__ constexpr size_t smem_model() { return align16(sizeof(ModelT<real>)); }
+constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
+template <typename real> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)TB_WARPS * EPW * align16(sizeof(EnvSh<real>)); }
 
-// One warp per env, persistent CTAs: the grid is sized to fill the machine once (SMs x resident CTAs) and every
-// warp pulls env indices from a global counter until the batch is done, so envs of different cost (contact
-// count, Newton iterations, resets) balance dynamically and the model constants are staged once per CTA in
-// shared memory (lane-indexed reads of them would serialise in the constant cache).  Warps never synchronise
-// with each other after that.
-template <int MODE, int SHAPE = 0>
-__global__ void __launch_bounds__(Shape<SHAPE>::WARPS * 32, Shape<SHAPE>::MIN_CTAS) tsg_env_kernel(const DevModel* __restrict__ gm,
-                                                                  const EnvCfg* __restrict__ gc, StepIO io,
-                                                                  Con* __restrict__ spill_base, int* __restrict__ counter) {
-  extern __shared__ __align__(16) unsigned char tsg_smem[];
-  unsigned char* smem = tsg_smem;
+// Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every warp pulls chunks of EPW
+// consecutive envs (then pool slots) from a global counter until the batch is done, so chunks of different cost
+// (contact count, Newton iterations, resets) balance dynamically.  The model constants are staged once per CTA in
+// shared memory.  Warps never synchronise with each other after that.
+template <typename real, int MODE>
+__global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<real>* __restrict__ gm,
+                                                                            const EnvCfg* __restrict__ gc, StepIO io) {
+  extern __shared__ __align__(16) unsigned char tb_smem[];
   {
-    const double* src = reinterpret_cast<const double*>(gm);
-    double* dst = reinterpret_cast<double*>(smem);
-    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 8); i += blockDim.x) dst[i] = src[i];
-    src = reinterpret_cast<const double*>(gc);
-    dst = reinterpret_cast<double*>(smem + SMEM_MODEL);
-    for (int i = threadIdx.x; i < (int)(sizeof(EnvCfg) / 8); i += blockDim.x) dst[i] = src[i];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gm);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tb_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelT<real>) / 4); i += blockDim.x) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t*>(gc);
+    dst = reinterpret_cast<uint32_t*>(tb_smem + smem_model<real>());
+    for (int i = threadIdx.x; i < (int)(sizeof(EnvCfg) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const DevModel& m = *reinterpret_cast<const DevModel*>(smem);
-  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(smem + SMEM_MODEL);
-  int warp = threadIdx.x / TSG_VW, lane = threadIdx.x % TSG_VW;  // virtual warp / lane
-  EnvScratch& S = *reinterpret_cast<EnvScratch*>(smem + SMEM_MODEL + SMEM_CFG + warp * SMEM_SCRATCH);
-  constexpr int VWARPS = Shape<SHAPE>::VWARPS;
-  if (lane == 0) S.spill = spill_base + (size_t)(blockIdx.x * VWARPS + warp) * (MAXC - MAXC_S);
-  WSYNC();
-  // items: the n_envs envs, then (STEP: every launch, RESET of all envs: prewarm) the background reset pool slots
-  int n_items = io.n_envs + ((MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? io.n_pool : 0);
-  int first = 0;  // first item of the unaligned loop below
-#if TSG_ALIGNED
-  // aligned work loop over the envs: the envs of one alignment scope (physical warp / CTA) are fetched together and
-  // walk through the step in phase; a (virtual) warp without an env at the tail runs the idle barrier protocol.
-  if (MODE == MODE_STEP) {
-#ifdef TSG_ALIGN_WARP
-    constexpr int GROUP = 32 / TSG_VW;
-    for (;;) {
-      int base = 0;
-      if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, GROUP);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= io.n_envs) break;
-      int e = base + (threadIdx.x & 31) / TSG_VW;
-#else
-    __shared__ int s_base;
-    for (;;) {
-      if (threadIdx.x == 0) s_base = atomicAdd(counter, VWARPS);
-      __syncthreads();
-      int e = s_base + warp;
-      __syncthreads();
-      if (e - warp >= n_items) break;
-#endif
-      if (lane == 0) S.align = 1;
-      WSYNC();
-      if (e < io.n_envs) run_step(S, m, c, io, e, lane);
-      else {
-        // background reset pool slot: a slot that is warming up runs its one warm-up env step of this launch in
-        // phase with the group (same barrier protocol as an env step); ready slots and the tail idle through it
-        bool warming = false;
-        if (e < n_items) warming = (int)io.state[(size_t)e * STATE_STRIDE + SO_FLAGS] <= c.warmup_steps;
-        if (warming) run_pool(S, m, c, io, e - io.n_envs, false, lane);
-        else for (int s = 0; s < c.frame_skip; s++) aligned_idle_substep();
-      }
-    }
-    first = n_items;
-    counter += 1;  // (nothing is left for the unaligned loop of a step launch)
-  }
-#endif
-  if (lane == 0) S.align = 0;
-  WSYNC();
+  const ModelT<real>& m = *reinterpret_cast<const ModelT<real>*>(tb_smem);
+  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tb_smem + smem_model<real>());
+  const LaneCtx L = make_lane();
+  const int warp = threadIdx.x >> 5;
+  EnvSh<real>& S = *reinterpret_cast<EnvSh<real>*>(tb_smem + smem_model<real>() + SMEM_CFG +
+                                                   (size_t)(warp * EPW + L.grp) * align16(sizeof(EnvSh<real>)));
+  const int env_chunks = (io.n_envs + EPW - 1) / EPW;
+  const int pool_chunks = (MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? (io.n_pool + EPW - 1) / EPW : 0;
   for (;;) {
-    int e = 0;
-    if (lane == 0) e = first + atomicAdd(counter, 1);
-    e = __shfl_sync(TSG_VMASK(), e, 0, TSG_VW);
-    if (e >= n_items) break;
-    if (e >= io.n_envs) { run_pool(S, m, c, io, e - io.n_envs, MODE == MODE_RESET, lane); WSYNC(); continue; }
-    if (MODE == MODE_RESET && io.mask && !io.mask[e]) continue;
-    if (MODE == MODE_STEP) run_step(S, m, c, io, e, lane);
-    else if (MODE == MODE_RESET) run_reset(S, m, c, io, e, lane);
-    else run_forward(S, m, c, io, e, lane);
-    WSYNC();
+    int chunk = 0;
+    if (L.lane == 0) chunk = atomicAdd(io.counter, 1);
+    chunk = shfl(chunk, 0);
+    if (chunk >= env_chunks + pool_chunks) break;
+    if (chunk < env_chunks) {
+      if (MODE == MODE_STEP) run_step(S, m, c, io, L, chunk * EPW);
+      else if (MODE == MODE_RESET) run_reset(S, m, c, io, L, chunk * EPW);
+      else run_forward(S, m, c, io, L, chunk * EPW);
+    } else run_pool(S, m, c, io, L, (chunk - env_chunks) * EPW, MODE == MODE_RESET);
   }
 }
 
@@ -126,7 +75,7 @@ __global__ void __launch_bounds__(Shape<SHAPE>::WARPS * 32, Shape<SHAPE>::MIN_CT
 __global__ void __launch_bounds__(1024) tsg_assign_kernel(double* __restrict__ state, double* __restrict__ heading,
                                                            const uint8_t* __restrict__ done, uint8_t* __restrict__ need_sync,
                                                            double* obs, float* obs32, double* term_obs,
-                                                           const double* __restrict__ pool_obs, int* __restrict__ lists,
+                                                           const double* __restrict__ pool_obs, const double* __restrict__ pool_real_obs, double* real_obs, int* __restrict__ lists,
                                                            int* __restrict__ counts, int n, int n_pool, int obs_dim, int ready_phase) {
   __shared__ int wcount[32], woff[32], s_ndone, s_nready;
   int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -171,6 +120,7 @@ __global__ void __launch_bounds__(1024) tsg_assign_kernel(double* __restrict__ s
       double v = pool_obs[(size_t)p * obs_dim + i];
       if (obs) { if (term_obs) term_obs[(size_t)e * obs_dim + i] = obs[(size_t)e * obs_dim + i]; obs[(size_t)e * obs_dim + i] = v; }
       if (obs32) obs32[(size_t)e * obs_dim + i] = (float)v;
+      if (real_obs && pool_real_obs) real_obs[(size_t)e * obs_dim + i] = pool_real_obs[(size_t)p * obs_dim + i];
     }
     if (lane == 0) { src[SO_FLAGS] = 0; src[SO_NRESET] += 1; dst[SO_NRESET] += 1; if (need_sync) need_sync[e] = 0; }
   }
@@ -199,35 +149,36 @@ __global__ void tsg_scatter_kernel(double* __restrict__ state, int n, const doub
   if (ctrl) for (int i = 0; i < NACT; i++) r[SO_CTRL + i] = ctrl[(size_t)e * NACT + i];
   if (act) for (int i = 0; i < NACT; i++) r[SO_ACT + i] = act[(size_t)e * NACT + i];
 }
-__global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const DevModel* m) {  // n = envs + pool slots
+__global__ void tsg_init_records_kernel(double* __restrict__ state, int n, const double* qpos0) {  // n = envs + pool slots
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   double* r = state + (size_t)e * STATE_STRIDE;
   for (int i = 0; i < STATE_STRIDE; i++) r[i] = 0;
-  for (int i = 0; i < NQ; i++) r[SO_QPOS + i] = m->qpos0[i];
+  for (int i = 0; i < NQ; i++) r[SO_QPOS + i] = qpos0[i];
 }
 
 // ------------------------------------------------------------------ handle
 struct TsgHandle {
-  int device, n_envs, n_pool, obs_dim, launches, ready_phase;
+  int device, n_envs, n_pool, obs_dim, launches, ready_phase, precision;
   long long env_id_base;
-  DevModel* d_model; EnvCfg* d_cfg; float* d_hdata;
+  void* d_model; EnvCfg* d_cfg; float* d_hdata; double* d_qpos0;
   double* d_state; double* d_heading; double* d_draws;
   uint8_t* d_done;
   // staging for the host-buffer entry points
   double *d_ctrl, *d_obs, *d_reward, *d_info, *d_termobs, *d_tmp;
   uint8_t* d_mask;
-  Con* d_spill; int* d_counter;
-  double* d_pool_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
+  int* d_counter;
+  double* d_pool_obs; double* d_pool_real_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
   double* d_realobs_own;
-  int grid[3], grid_step1, shape;   // shape: CTA shape of the step kernel (Shape<>), grid_step1: its grid for shape 1
+  int grid[3], regs;
+  size_t smem;
   cudaStream_t own_stream;
 };
 
 static thread_local std::string g_err;
 const char* tsg_last_error(void) { return g_err.c_str(); }
-int tsg_version(void) { return 1; }
+int tsg_version(void) { return 2; }
 int tsg_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 
 #define CK(call)                                                                    \
@@ -246,78 +197,73 @@ static size_t extra_smem() {
   if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
   return (size_t)v;
 }
-template <int MODE, int SHAPE>
-static int launch_shape(TsgHandle* h, const StepIO& io, cudaStream_t s, int grid) {
-  CK(cudaMemsetAsync(h->d_counter, 0, 2 * sizeof(int), s));
-  tsg_env_kernel<MODE, SHAPE><<<grid, Shape<SHAPE>::WARPS * 32, smem_of<SHAPE>() + extra_smem(), s>>>(h->d_model, h->d_cfg, io, h->d_spill, h->d_counter);
+template <typename real, int MODE>
+static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
+  io.counter = h->d_counter + counter_slot;
+  tb_env_kernel<real, MODE><<<h->grid[MODE], TB_WARPS * 32, smem_bytes<real>() + extra_smem(), s>>>(
+      (const ModelT<real>*)h->d_model, h->d_cfg, io);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
 }
+// counter_slot: which of the handle's work counters the launch consumes (they are zeroed together, once per API call)
 template <int MODE>
-static int launch_env(TsgHandle* h, const StepIO& io, cudaStream_t s) {
-  if (MODE == MODE_STEP && h->shape == 1) return launch_shape<MODE_STEP, 1>(h, io, s, h->grid_step1);
-  return launch_shape<MODE, 0>(h, io, s, h->grid[MODE]);
+static int launch_env(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
+  return h->precision == TSG_PRECISION_F32 ? launch_t<float, MODE>(h, io, s, counter_slot) : launch_t<double, MODE>(h, io, s, counter_slot);
 }
-template <int MODE, int SHAPE>
-static int setup_kernel(TsgHandle* h, int num_sms, int* grid, int* max_spill_warps) {
-  CK(cudaFuncSetAttribute(tsg_env_kernel<MODE, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_of<SHAPE>() + extra_smem())));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tsg_env_kernel<MODE, SHAPE>, Shape<SHAPE>::WARPS * 32, smem_of<SHAPE>() + extra_smem()));
-  if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
-  // The shared-memory carve-out is left to the driver's default (the smallest configuration that holds the resident
-  // CTAs): what is not carved out stays L1, which serves the per-thread stack and the contact spill area.  With 2
-  // contact slots per env the 3 CTAs fit the 164 KB configuration (92 KB L1) instead of 196 KB: +5 % (profiles/).
-  constexpr int VW = vwarps_of<SHAPE>();
-  int need = (h->n_envs + h->n_pool + VW - 1) / VW, full = num_sms * per_sm;
-  *grid = need < full ? need : full;
-  if (*grid * VW > *max_spill_warps) *max_spill_warps = *grid * VW;
+static int zero_counters(TsgHandle* h, cudaStream_t s) {
+  CK(cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), s));
   return 0;
 }
-// which CTA shape steps this handle's batch faster: waves needed x measured time of one wave (ms, B200, profiles/)
-static int pick_shape(int n_envs, int num_sms) {
-  const char* e = getenv("TSG_SHAPE");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
-  auto waves = [&](int warps, int ctas) { int groups = (n_envs + warps - 1) / warps, slots = num_sms * ctas; return (groups + slots - 1) / slots; };
-  double t0 = waves(Shape<0>::WARPS, Shape<0>::MIN_CTAS) * 5.0, t1 = waves(Shape<1>::WARPS, Shape<1>::MIN_CTAS) * 6.4;
-  return t1 < t0 ? 1 : 0;
+template <typename real, int MODE>
+static int setup_kernel(TsgHandle* h, int num_sms) {
+  size_t smem = smem_bytes<real>() + extra_smem();
+  CK(cudaFuncSetAttribute(tb_env_kernel<real, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<real, MODE>, TB_WARPS * 32, smem));
+  if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
+  // what is not carved out for shared memory stays L1, which serves the lanes' local memory (contacts, spills)
+  int chunks = (h->n_envs + EPW - 1) / EPW + (h->n_pool + EPW - 1) / EPW;
+  int need = (chunks + TB_WARPS - 1) / TB_WARPS, full = num_sms * per_sm;
+  h->grid[MODE] = need < full ? need : full;
+  if (MODE == MODE_STEP) {
+    cudaFuncAttributes a;
+    CK(cudaFuncGetAttributes(&a, tb_env_kernel<real, MODE>));
+    h->regs = a.numRegs; h->smem = smem;
+  }
+  return 0;
+}
+template <typename real>
+static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
+  ModelT<real> dm;
+  std::string err = make_model<real>(*model, dm, h->d_hdata);
+  if (!err.empty()) FAIL("tsg_create: " + err);
+  CK(cudaMalloc(&h->d_model, sizeof(dm)));
+  CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
+  if (setup_kernel<real, MODE_STEP>(h, sms) || setup_kernel<real, MODE_RESET>(h, sms) || setup_kernel<real, MODE_FORWARD>(h, sms)) return -2;
+  return 0;
 }
 
-int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int device, long long env_id_base,
-               TsgHandle** out) {
-  return tsg_create_pooled(model, cfg, n_envs, 0, device, env_id_base, out);
-}
-int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int n_pool, int device,
-                      long long env_id_base, TsgHandle** out) {
-  if (!model || !cfg || !out) FAIL("tsg_create: null argument");
-  if (n_envs < 1) FAIL("tsg_create: n_envs must be >= 1");
-  if (n_pool < 0) FAIL("tsg_create: n_pool must be >= 0");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); FAIL("tsg_create: no CUDA device (libtsg has no CPU path)"); }
-  if (device < 0 || device >= ndev) FAIL("tsg_create: bad device index");
-  CK(cudaSetDevice(device));
+static int create_impl(TsgHandle* h, const TsgModel* model, const TsgEnvConfig* cfg) {
+  const int n_envs = h->n_envs, n_pool = h->n_pool;
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  CK(cudaGetDeviceProperties(&prop, h->device));
   if (prop.major < 10) FAIL("tsg_create: libtsg is built for sm_100a (B200) only");
-  TsgHandle* h = new TsgHandle();
-  memset(h, 0, sizeof(*h));
-  h->device = device; h->n_envs = n_envs; h->n_pool = n_pool; h->env_id_base = env_id_base;
   if (model->floor_type == TSG_FLOOR_HFIELD) {
-    if (!model->hf_data) { delete h; FAIL("tsg_create: height field data missing"); }
+    if (!model->hf_data) FAIL("tsg_create: height field data missing");
     size_t nb = (size_t)model->hf_nrow * model->hf_ncol * sizeof(float);
     CK(cudaMalloc(&h->d_hdata, nb));
     CK(cudaMemcpy(h->d_hdata, model->hf_data, nb, cudaMemcpyHostToDevice));
   }
-  DevModel dm; EnvCfg ec;
-  std::string err = make_dev_model(*model, dm, h->d_hdata);
-  if (err.empty()) err = make_env_cfg(*cfg, *model, ec);
-  if (!err.empty()) { tsg_destroy(h); FAIL("tsg_create: " + err); }
+  EnvCfg ec;
+  std::string err = make_env_cfg(*cfg, *model, ec);
+  if (!err.empty()) FAIL("tsg_create: " + err);
   h->obs_dim = ec.obs_dim; h->ready_phase = ec.warmup_steps + 1;
   size_t n = (size_t)n_envs + (size_t)n_pool;
-  CK(cudaMalloc(&h->d_model, sizeof(DevModel)));
   CK(cudaMalloc(&h->d_cfg, sizeof(EnvCfg)));
-  CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_cfg, &ec, sizeof(ec), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_qpos0, NQ * sizeof(double)));
+  CK(cudaMemcpy(h->d_qpos0, model->qpos0, NQ * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_state, n * STATE_STRIDE * sizeof(double)));
   CK(cudaMalloc(&h->d_heading, n * HEADING_SLOTS * sizeof(double)));
   CK(cudaMalloc(&h->d_draws, n * NDRAW * sizeof(double)));
@@ -325,13 +271,10 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
   CK(cudaMemset(h->d_heading, 0, n * HEADING_SLOTS * sizeof(double)));
   CK(cudaMemset(h->d_draws, 0, n * NDRAW * sizeof(double)));
   CK(cudaMemset(h->d_done, 0, n));
-  int spill_warps = 0, sms = prop.multiProcessorCount;
-  h->shape = (TSG_VW == 32) ? pick_shape(n_envs, sms) : 0;
-  if (setup_kernel<MODE_STEP, 0>(h, sms, &h->grid[MODE_STEP], &spill_warps) || setup_kernel<MODE_STEP, 1>(h, sms, &h->grid_step1, &spill_warps) ||
-      setup_kernel<MODE_RESET, 0>(h, sms, &h->grid[MODE_RESET], &spill_warps) ||
-      setup_kernel<MODE_FORWARD, 0>(h, sms, &h->grid[MODE_FORWARD], &spill_warps)) { tsg_destroy(h); return -2; }
-  CK(cudaMalloc(&h->d_spill, (size_t)spill_warps * (MAXC - MAXC_S) * sizeof(Con)));
-  CK(cudaMalloc(&h->d_counter, 2 * sizeof(int)));
+  int rc = h->precision == TSG_PRECISION_F32 ? setup_model<float>(h, model, prop.multiProcessorCount)
+                                             : setup_model<double>(h, model, prop.multiProcessorCount);
+  if (rc) return rc;
+  CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   if (ec.use_obs_noise) {   // the noise-free observation always has a home; tsg_set_real_obs redirects it
     CK(cudaMalloc(&h->d_realobs_own, (size_t)n_envs * ec.obs_dim * sizeof(double)));
@@ -340,14 +283,41 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
   }
   if (n_pool) {
     CK(cudaMalloc(&h->d_pool_obs, (size_t)n_pool * ec.obs_dim * sizeof(double)));
+    if (ec.use_obs_noise) CK(cudaMalloc(&h->d_pool_real_obs, (size_t)n_pool * ec.obs_dim * sizeof(double)));
     CK(cudaMalloc(&h->d_lists, (size_t)2 * n_pool * sizeof(int)));
     CK(cudaMalloc(&h->d_counts, 4 * sizeof(int)));
     CK(cudaMemset(h->d_counts, 0, 4 * sizeof(int)));
     CK(cudaMalloc(&h->d_need_sync, n_envs));
   }
-  tsg_init_records_kernel<<<((int)n + 127) / 128, 128>>>(h->d_state, (int)n, h->d_model);
+  tsg_init_records_kernel<<<((int)n + 127) / 128, 128>>>(h->d_state, (int)n, h->d_qpos0);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int tsg_create(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int device, long long env_id_base,
+               TsgHandle** out) {
+  return tsg_create_opts(model, cfg, n_envs, 0, device, env_id_base, TSG_PRECISION_F64, out);
+}
+int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int n_pool, int device,
+                      long long env_id_base, TsgHandle** out) {
+  return tsg_create_opts(model, cfg, n_envs, n_pool, device, env_id_base, TSG_PRECISION_F64, out);
+}
+int tsg_create_opts(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs, int n_pool, int device,
+                    long long env_id_base, int precision, TsgHandle** out) {
+  if (!model || !cfg || !out) FAIL("tsg_create: null argument");
+  if (n_envs < 1) FAIL("tsg_create: n_envs must be >= 1");
+  if (n_pool < 0) FAIL("tsg_create: n_pool must be >= 0");
+  if (precision != TSG_PRECISION_F64 && precision != TSG_PRECISION_F32) FAIL("tsg_create: bad precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); FAIL("tsg_create: no CUDA device (libtsg has no CPU path)"); }
+  if (device < 0 || device >= ndev) FAIL("tsg_create: bad device index");
+  CK(cudaSetDevice(device));
+  TsgHandle* h = new TsgHandle();
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->n_envs = n_envs; h->n_pool = n_pool; h->env_id_base = env_id_base; h->precision = precision;
+  int rc = create_impl(h, model, cfg);
+  if (rc) { std::string keep = g_err; tsg_destroy(h); g_err = keep; return rc; }   // no leak on a failed create
   *out = h;
   return 0;
 }
@@ -355,8 +325,9 @@ int tsg_create_pooled(const TsgModel* model, const TsgEnvConfig* cfg, int n_envs
 int tsg_destroy(TsgHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
-                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_spill, h->d_counter, h->d_pool_obs, h->d_lists, h->d_counts, h->d_need_sync, h->d_realobs_own};
+  void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_qpos0, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_counter, h->d_pool_obs,
+                  h->d_pool_real_obs, h->d_lists, h->d_counts, h->d_need_sync, h->d_realobs_own};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -365,6 +336,7 @@ int tsg_destroy(TsgHandle* h) {
 int tsg_num_envs(const TsgHandle* h) { return h ? h->n_envs : -1; }
 int tsg_obs_dim(const TsgHandle* h) { return h ? h->obs_dim : -1; }
 int tsg_launches(const TsgHandle* h) { return h ? h->launches : -1; }
+int tsg_precision(const TsgHandle* h) { return h ? h->precision : -1; }
 int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
   if (!h || !counts3) FAIL("tsg_pool_stats_host: null argument");
   counts3[0] = counts3[1] = counts3[2] = 0;
@@ -374,17 +346,11 @@ int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
   CK(cudaMemcpy(counts3, h->d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
 }
-int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes, int* regs_per_thread) {
-  (void)h;
-  int w = h->shape == 1 ? Shape<1>::WARPS : Shape<0>::WARPS;
-  if (warps_per_cta) *warps_per_cta = w * 100 + TSG_VW;  // physical warps per CTA * 100 + lanes per env
-  if (smem_bytes) *smem_bytes = (int)(h->shape == 1 ? smem_of<1>() : smem_of<0>());
-  if (regs_per_thread) {
-    cudaFuncAttributes a;
-    if (h->shape == 1) CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP, 1>));
-    else CK(cudaFuncGetAttributes(&a, tsg_env_kernel<MODE_STEP, 0>));
-    *regs_per_thread = a.numRegs;
-  }
+int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes_out, int* regs_per_thread) {
+  if (!h) FAIL("tsg_kernel_config: null handle");
+  if (warps_per_cta) *warps_per_cta = TB_WARPS * 100 + G;  // warps per CTA * 100 + lanes per env
+  if (smem_bytes_out) *smem_bytes_out = (int)h->smem;
+  if (regs_per_thread) *regs_per_thread = h->regs;
   return 0;
 }
 
@@ -393,7 +359,7 @@ static StepIO base_io(TsgHandle* h) {
   memset(&io, 0, sizeof(io));
   io.state = h->d_state; io.heading = h->d_heading; io.draws = h->d_draws;
   io.n_envs = h->n_envs; io.env_id_base = h->env_id_base;
-  io.n_pool = h->n_pool; io.pool_obs = h->d_pool_obs;
+  io.n_pool = h->n_pool; io.pool_obs = h->d_pool_obs; io.pool_real_obs = h->d_pool_real_obs;
   io.real_obs = h->real_obs;
   return io;
 }
@@ -409,7 +375,8 @@ int tsg_reset(TsgHandle* h, const uint8_t* mask_dev, unsigned long long seed, co
     CK(cudaMemcpyAsync(h->d_draws, draws_in_dev, (size_t)h->n_envs * NDRAW * sizeof(double), cudaMemcpyDeviceToDevice, s));
     io.explicit_draws = 1;
   }
-  return launch_env<MODE_RESET>(h, io, s);
+  if (zero_counters(h, s)) return -2;
+  return launch_env<MODE_RESET>(h, io, s, 0);
 }
 
 int tsg_step(TsgHandle* h, const void* ctrl_dev, int ctrl_dtype, double* obs_dev, float* obs32_dev, double* reward_dev,
@@ -426,20 +393,22 @@ int tsg_step(TsgHandle* h, const void* ctrl_dev, int ctrl_dtype, double* obs_dev
   io.done = done_dev ? done_dev : h->d_done;
   io.seed = seed;
   if (!auto_reset) io.n_pool = 0;  // the pool only advances on auto-resetting handles
-  int rc = launch_env<MODE_STEP>(h, io, s);
+  if (zero_counters(h, s)) return -2;   // one memset serves the step launch and the reset launch that may follow
+  int rc = launch_env<MODE_STEP>(h, io, s, 0);
   if (rc) return rc;
   if (auto_reset) {
     const uint8_t* mask = io.done;
     if (h->n_pool) {  // hand pre-warmed slots to the done envs; only the remainder resets synchronously
       tsg_assign_kernel<<<1, 1024, 0, s>>>(h->d_state, h->d_heading, io.done, h->d_need_sync, obs_dev, obs32_dev, term_obs_dev,
-                                           h->d_pool_obs, h->d_lists, h->d_counts, h->n_envs, h->n_pool, h->obs_dim, h->ready_phase);
+                                           h->d_pool_obs, h->d_pool_real_obs, h->real_obs, h->d_lists, h->d_counts, h->n_envs,
+                                           h->n_pool, h->obs_dim, h->ready_phase);
       CK(cudaGetLastError());
       h->launches++;
       mask = h->d_need_sync;
     }
     StepIO r = base_io(h);
     r.mask = mask; r.seed = seed; r.obs = obs_dev; r.obs32 = obs32_dev; r.term_obs = term_obs_dev;
-    rc = launch_env<MODE_RESET>(h, r, s);
+    rc = launch_env<MODE_RESET>(h, r, s, 1);   // warps whose ten envs need no reset leave after one mask read
   }
   return rc;
 }
@@ -454,6 +423,7 @@ int tsg_get_real_obs_host(TsgHandle* h, double* real_obs) {
   if (!h || !real_obs) FAIL("tsg_get_real_obs_host: null argument");
   if (!h->real_obs) FAIL("tsg_get_real_obs_host: the handle was created without use_obs_noise");
   CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(real_obs, h->real_obs, (size_t)h->n_envs * h->obs_dim * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -463,13 +433,28 @@ int tsg_forward(TsgHandle* h, double* obs_dev, double* info_dev, void* stream) {
   CK(cudaSetDevice(h->device));
   StepIO io = base_io(h);
   io.obs = obs_dev; io.info = info_dev;
-  return launch_env<MODE_FORWARD>(h, io, (cudaStream_t)stream);
+  if (zero_counters(h, (cudaStream_t)stream)) return -2;
+  return launch_env<MODE_FORWARD>(h, io, (cudaStream_t)stream, 0);
 }
 
 // ---- host-buffer helpers
 static int ensure(double** p, size_t count) {
   if (*p) return 0;
   CK(cudaMalloc(p, count * sizeof(double)));
+  return 0;
+}
+// mj_forward after a host-side state write, on the handle's own stream, synchronous (set_state of the single-env API)
+int tsg_forward_host(TsgHandle* h, double* obs, double* info) {
+  if (!h) FAIL("tsg_forward_host: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t n = h->n_envs, od = h->obs_dim;
+  if (ensure(&h->d_obs, n * od) || ensure(&h->d_info, n * INFO_DIM)) return -2;
+  cudaStream_t s = h->own_stream;
+  int rc = tsg_forward(h, h->d_obs, h->d_info, s);
+  if (rc) return rc;
+  if (obs) CK(cudaMemcpyAsync(obs, h->d_obs, n * od * 8, cudaMemcpyDeviceToHost, s));
+  if (info) CK(cudaMemcpyAsync(info, h->d_info, n * INFO_DIM * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }
 int tsg_get_state_host(TsgHandle* h, double* qpos, double* qvel, double* act, double* warm, double* ctrl) {
@@ -519,6 +504,21 @@ int tsg_set_records_host(TsgHandle* h, const double* records) {
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(h->d_state, records, (size_t)h->n_envs * STATE_STRIDE * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+// the heading rings the records' cursors (head_n / head_pos) point into: part of an env-state checkpoint
+int tsg_get_heading_host(TsgHandle* h, double* heading) {
+  if (!h || !heading) FAIL("tsg_get_heading_host: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(heading, h->d_heading, (size_t)h->n_envs * HEADING_SLOTS * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int tsg_set_heading_host(TsgHandle* h, const double* heading) {
+  if (!h || !heading) FAIL("tsg_set_heading_host: null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(h->d_heading, heading, (size_t)h->n_envs * HEADING_SLOTS * 8, cudaMemcpyHostToDevice));
   return 0;
 }
 int tsg_get_draws_host(TsgHandle* h, double* draws) {

@@ -156,7 +156,7 @@ class _SingleEnv:
         q = np.ascontiguousarray(np.asarray(qpos, np.float64).reshape(1, 21))
         v = np.ascontiguousarray(np.asarray(qvel, np.float64).reshape(1, 18))
         _lib.check(self.L.tsg_set_state_host(self.h, self._p(q), self._p(v), None, None, None))
-        _lib.check(self.L.tsg_forward(self.h, None, None, None))
+        _lib.check(self.L.tsg_forward_host(self.h, None, None))   # own stream, synchronous: ordered with step / reset
 
     def render(self):
         return None

@@ -15,7 +15,9 @@ INFO = dict(rew_fwd=0, rew_ctrl=1, rew_survive=2, x=3, y=4, psi=5, xvel=6, yvel=
 SYMBOLS = ["tsg_last_error", "tsg_version", "tsg_device_count", "tsg_create", "tsg_create_pooled", "tsg_pool_stats_host", "tsg_destroy", "tsg_num_envs",
            "tsg_obs_dim", "tsg_launches", "tsg_kernel_config", "tsg_reset", "tsg_step", "tsg_forward",
            "tsg_get_state_host", "tsg_set_state_host", "tsg_get_records_host", "tsg_set_records_host",
-           "tsg_get_draws_host", "tsg_step_host", "tsg_reset_host", "tsg_set_real_obs", "tsg_get_real_obs_host"]
+           "tsg_get_draws_host", "tsg_step_host", "tsg_reset_host", "tsg_set_real_obs", "tsg_get_real_obs_host",
+           "tsg_create_opts", "tsg_precision", "tsg_forward_host", "tsg_get_heading_host", "tsg_set_heading_host"]
+PRECISION = {"f64": 0, "f32": 1}
 
 
 class TsgError(RuntimeError):
@@ -33,14 +35,18 @@ def load():
     if not os.path.isfile(so):
         raise TsgError(f"{so} not built: run `python -m tensegrity_rl_b200.build` (needs nvcc); "
                        "there is no CPU fallback")
+    if so == _build.SO and _build.is_stale():   # an .so built from other sources would load with a silent ABI skew
+        raise TsgError(f"{so} is stale (sources or flags changed since it was built): "
+                       "run `python -m tensegrity_rl_b200.build`")
     L = C.CDLL(so)
     vp, dp, fp, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     L.tsg_last_error.restype = C.c_char_p
     L.tsg_create.argtypes = [C.POINTER(TsgModel), C.POINTER(TsgEnvConfig), C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
     L.tsg_create_pooled.argtypes = [C.POINTER(TsgModel), C.POINTER(TsgEnvConfig), C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(vp)]
+    L.tsg_create_opts.argtypes = [C.POINTER(TsgModel), C.POINTER(TsgEnvConfig), C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(vp)]
     L.tsg_pool_stats_host.argtypes = [vp, C.POINTER(C.c_int)]
     L.tsg_destroy.argtypes = [vp]
-    for f in ("tsg_num_envs", "tsg_obs_dim", "tsg_launches"):
+    for f in ("tsg_num_envs", "tsg_obs_dim", "tsg_launches", "tsg_precision"):
         getattr(L, f).argtypes = [vp]
     L.tsg_kernel_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.tsg_reset.argtypes = [vp, u8p, C.c_ulonglong, dp, dp, fp, dp, vp]
@@ -51,6 +57,9 @@ def load():
     L.tsg_get_records_host.argtypes = [vp, dp]
     L.tsg_set_records_host.argtypes = [vp, dp]
     L.tsg_get_draws_host.argtypes = [vp, dp]
+    L.tsg_forward_host.argtypes = [vp, dp, dp]
+    L.tsg_get_heading_host.argtypes = [vp, dp]
+    L.tsg_set_heading_host.argtypes = [vp, dp]
     L.tsg_step_host.argtypes = [vp, dp, dp, dp, u8p, dp, C.c_int, C.c_ulonglong, dp]
     L.tsg_reset_host.argtypes = [vp, u8p, C.c_ulonglong, dp, dp]
     L.tsg_set_real_obs.argtypes = [vp, dp]

@@ -26,10 +26,11 @@ class TensegrityVecEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, num_envs, xml_file=None, env="tr_env", device=0, seed=0, env_id_base=0,
-                 auto_reset=True, info_mode="auto", max_episode_steps=5000, reset_pool=0, **env_kwargs):
+                 auto_reset=True, info_mode="auto", max_episode_steps=5000, reset_pool=0, precision="f64", **env_kwargs):
         """reset_pool: number of background reset slots (0 = every reset runs synchronously, bit-reproducible per
         env id; "auto" = num_envs // 4, at least 32).  With a pool, an env that is done receives a slot that has
-        already been through the reference's 50-step reset warm-up, so resets add no latency to a step."""
+        already been through the reference's 50-step reset warm-up, so resets add no latency to a step.
+        precision: "f64" (the reference's arithmetic, default) or "f32" (optional fp32 physics)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -54,8 +55,9 @@ class TensegrityVecEnv:
         if reset_pool == "auto":
             reset_pool = max(32, self.num_envs // 4) if auto_reset else 0
         self.reset_pool = int(reset_pool)
-        _lib.check(self.L.tsg_create_pooled(C.byref(self._model), C.byref(self.cfg), self.num_envs, self.reset_pool,
-                                            self.device_index, int(env_id_base), C.byref(h)))
+        self.precision = precision
+        _lib.check(self.L.tsg_create_opts(C.byref(self._model), C.byref(self.cfg), self.num_envs, self.reset_pool,
+                                          self.device_index, int(env_id_base), _lib.PRECISION[precision], C.byref(h)))
         self.h = h
         lo, hi = self.md["ctrlrange"]
         self.action_space = Box(np.full(6, lo, np.float32), np.full(6, hi, np.float32), dtype=np.float32)
@@ -195,6 +197,17 @@ class TensegrityVecEnv:
         rec = np.ascontiguousarray(rec, np.float64)
         assert rec.shape == (self.num_envs, _lib.STATE_STRIDE)
         _lib.check(self.L.tsg_set_records_host(self.h, C.c_void_p(rec.ctypes.data)))
+
+    def get_heading(self):
+        """heading rings (turn / aiming reward delay): records + heading rings = a checkpoint of the env state"""
+        hd = np.zeros((self.num_envs, _lib.HEADING_SLOTS))
+        _lib.check(self.L.tsg_get_heading_host(self.h, C.c_void_p(hd.ctypes.data)))
+        return hd
+
+    def set_heading(self, hd):
+        hd = np.ascontiguousarray(hd, np.float64)
+        assert hd.shape == (self.num_envs, _lib.HEADING_SLOTS)
+        _lib.check(self.L.tsg_set_heading_host(self.h, C.c_void_p(hd.ctypes.data)))
 
     def get_draws(self):
         d = np.zeros((self.num_envs, _lib.NDRAW))

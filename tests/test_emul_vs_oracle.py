@@ -1,5 +1,6 @@
-"""CPU check of the CUDA SOURCE's lane logic: tsg_core.cuh / tsg_env.cuh compiled as a serial one-warp
-emulator (tests/emul) against the oracle.  The GPU twin of these tests is tests/test_gpu_parity.py."""
+"""CPU check of the CUDA SOURCE: csrc/tb_*.cuh compiled as plain C++ and run by a 32-lane fibre warp emulator
+(tests/emul: shuffles, votes and warp barriers are rendezvous points between the lanes) against the oracle.
+The GPU twin of these tests is tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
@@ -14,13 +15,10 @@ def _copy_state(mj, em):
     em.rec[63:69] = mj.act
 
 
-@pytest.mark.parametrize("reverse", [False, True])
 @pytest.mark.parametrize("model,lo,hi", [("flat", -0.45, -0.15), ("flat", -0.45, 0.15), ("uneven", -0.45, 0.15)])
-def test_single_step_state_parity(oracle, model, lo, hi, reverse):
-    """one env step (20 substeps) from identical (qpos, qvel, act, warmstart, ctrl): 1e-9 relative.
-    reverse=True runs the items of every lane loop in reverse order: a phase whose result depends on the item
-    order (an intra-phase read/write hazard that would be a race on the GPU) fails here."""
-    mj, em = oracle.MjLike(model), E.Emul(model, reverse=reverse)
+def test_single_step_state_parity(oracle, model, lo, hi):
+    """one env step (20 substeps) from identical (qpos, qvel, act, warmstart, ctrl): 1e-9 relative."""
+    mj, em = oracle.MjLike(model), E.Emul(model)
     rng = np.random.default_rng(5)
     worst = 0.0
     for st in range(60):
@@ -37,10 +35,42 @@ def test_single_step_state_parity(oracle, model, lo, hi, reverse):
     assert worst < 1e-9, worst
 
 
+@pytest.mark.parametrize("model", ["flat", "uneven"])
+def test_full_warp_of_desynchronised_envs(oracle, model):
+    """ten envs in one warp, each at a different point of its trajectory (different contact sets, Newton iteration and
+    line-search counts per substep): the predication that lets them share one instruction stream must not leak
+    between envs.  Every env is compared with its own oracle instance."""
+    n = 10
+    mjs = [oracle.MjLike(model) for _ in range(n)]
+    w = E.EmulWarp(model, n)
+    rng = np.random.default_rng(3)
+    for i, mj in enumerate(mjs):
+        for _ in range(2 * i + (30 if model == "uneven" else 0)):   # (the uneven model starts 1 m above its floor)
+            mj.ctrl[:] = rng.uniform(-0.45, -0.15, 6)
+            mj.step(20)
+    iters = set()
+    for st in range(6):
+        ctrl = rng.uniform(-0.45, -0.15, (n, 6))
+        for i, mj in enumerate(mjs):
+            w.rec[i, 0:21] = mj.qpos; w.rec[i, 21:39] = mj.qvel; w.rec[i, 39:57] = mj.qacc_warmstart; w.rec[i, 63:69] = mj.act
+            mj.ctrl[:] = ctrl[i]
+            mj.step(20)
+            mj.rne_post_constraint()
+        ten, cfrc, stats = w.mj_step(ctrl, 20)
+        for i, mj in enumerate(mjs):
+            assert np.abs(w.rec[i, 0:21] - mj.qpos).max() < 1e-9
+            assert np.abs(w.rec[i, 21:39] - mj.qvel).max() <= 1e-9 * max(1.0, np.abs(mj.qvel).max())
+            assert np.abs(ten[i] - mj.ten_length).max() < 1e-9
+            assert np.abs(cfrc[i] - mj.cfrc_ext).max() <= 1e-7 * max(1.0, np.abs(mj.cfrc_ext).max())
+            assert stats[i, 4] == 0 and stats[i, 5] == 0
+        iters.update(stats[:, 1].tolist())
+    assert len(iters) > 5   # the envs really did different amounts of solver work
+
+
 def test_conservative_prefilter_matches_unfiltered_oracle(oracle):
     """the CUDA source filters bar-bar pairs with an analytic capsule bound before MPR; the oracle runs MPR on
     every pair that passes MuJoCo's bounding-sphere test.  Squeeze the bars together and compare."""
-    mj, em = oracle.MjLike("flat"), E.Emul("flat", reverse=True)
+    mj, em = oracle.MjLike("flat"), E.Emul("flat")
     rng = np.random.default_rng(7)
     nbar = 0
     for st in range(80):
@@ -64,7 +94,7 @@ CASES = [("flat", "tr_env", "straight"), ("flat", "tr_env", "turn"), ("flat", "t
 def test_env_semantics_parity(xml, kind, task):
     rng = np.random.default_rng(11)
     oe = OracleEnv(xml, kind, desired_action=task)
-    em = E.Emul(xml, env_kind=kind, desired_action=task, reverse=(task in ("turn", "tracking")))
+    em = E.Emul(xml, env_kind=kind, desired_action=task)
     draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
     o1, o2 = oe.reset(draws), em.reset(draws)
     assert o1.shape == o2.shape == (oe.cfg.obs_dim,)
@@ -93,7 +123,7 @@ def test_philox_draws_are_keyed_by_env_and_reset_count():
     L = E.lib()
     def draws(seed, env, n):
         d = np.zeros(10)
-        L.emul_make_draws(E.P(d), C.c_ulonglong(seed), C.c_ulonglong(env), C.c_ulonglong(n))
+        L.tbe_make_draws(E.P(d), C.c_ulonglong(seed), C.c_ulonglong(env), C.c_ulonglong(n))
         return d
     a, b, c, d = draws(1, 5, 0), draws(1, 5, 0), draws(1, 6, 0), draws(1, 5, 1)
     assert np.array_equal(a, b) and not np.array_equal(a, c) and not np.array_equal(a, d)
@@ -103,10 +133,10 @@ def test_philox_draws_are_keyed_by_env_and_reset_count():
     assert abs(u[:, 2:8].mean()) < 0.03 and abs(u[:, 2:8].std() - 1) < 0.03
 
 
-def test_contact_spill_path(oracle):
-    """two bars pressed flat into the floor: 19 contacts, i.e. 17 beyond the shared-memory slots (MAXC_S = 2)
-    that live in the per-warp spill area; results must still match the dense oracle."""
-    mj, em = oracle.MjLike("flat"), E.Emul("flat", reverse=True)
+def test_many_contacts_per_bar(oracle):
+    """two bars pressed flat into the floor: 19 contacts (9-10 per bar, all owned by the bar's lane; the usual count
+    is 1); results must still match the dense oracle."""
+    mj, em = oracle.MjLike("flat"), E.Emul("flat")
     q = []
     for b in range(3):
         q += [0.0, 0.4 * b, 0.0375, np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0] if b < 2 else [0.0, 0.8, 3.0, 1, 0, 0, 0]
@@ -126,7 +156,7 @@ def test_obs_noise_parity(task):
     the same normal draws; the true observation (info["real_observation"]) and the reward are untouched by the noise."""
     rng = np.random.default_rng(3)
     oe = OracleEnv("flat", "tr_env", desired_action=task, use_obs_noise=True)
-    em = E.Emul("flat", env_kind="tr_env", desired_action=task, use_obs_noise=True, reverse=(task == "tracking"))
+    em = E.Emul("flat", env_kind="tr_env", desired_action=task, use_obs_noise=True)
     em.set_noise(77, 5)
     draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
     o_true, o_em = oe.reset(draws), em.reset(draws, seed=77, env_id=5)
