@@ -5,14 +5,17 @@
 // 9 two-site spatial tendons -> collision (plane / height field / bar-bar, MPR where MuJoCo uses libccd) -> condim-6
 // elliptic contact rows -> Newton with exact line search -> implicitfast -> advance.
 //
-// Mapping.  A bar's 13-number pose/velocity, its warm start, its 6x6 Newton block and every per-bar vector of the
-// solver live in the REGISTERS of the bar's lane for all frame_skip substeps; lanes exchange only what crosses bars
-// (tendon end points, world-frame twists, contact wrenches) through a ~1.9 KB per-env slice of shared memory and
-// 3-lane shuffle sums.  Contacts are owned by a lane (floor contacts by the bar's lane, bar-bar contacts by lane 2 of
-// the env) and kept in that lane's local memory, which the L1 caches at its actual use instead of a static worst-case
-// shared-memory reservation.  Control flow is WARP-UNIFORM: every data-dependent loop (Newton iterations, line-search
-// evaluations, second forward pass after a bad acceleration) runs while ANY env of the warp needs it, with the other
-// envs predicated off, so the 10 envs of a warp share every fetched instruction and never need a partial barrier.
+// Mapping.  A bar's pose / velocity / acceleration and every per-bar vector of the solver live in the REGISTERS of the
+// bar's lane for all frame_skip substeps.  Everything that crosses bars lives in the env's slice of SHARED memory:
+// world-frame poses and twists, the contacts (a small pool of slots per env; slots beyond it spill to a per-env global
+// area), and the 6x6 blocks of the Newton Hessian.  There are no per-lane local arrays on the hot path: local memory is
+// interleaved across the 32 lanes of a warp, so an array only one lane of an env uses still costs 32 lanes of cache.
+// Work that is naturally per contact is done by the lane that found the contact (its owner); work that is per bar
+// (wrench gathering, diagonal Hessian blocks, the bar's block row of the factorisation) by the bar's lane, so a
+// bar-bar contact is processed by up to three lanes in parallel.  Control flow is UNIFORM across the warp (optionally
+// across the CTA: TB_ALIGN): every data-dependent loop (Newton iterations, line-search evaluations, second forward
+// pass after a bad acceleration) runs while ANY env needs it, the others predicated off, so the envs of a warp share
+// every fetched instruction and never need a partial barrier.
 #pragma once
 #include "tb_mpr.h"
 
@@ -20,40 +23,53 @@ namespace tb {
 
 constexpr int G = 3;        // lanes per env
 constexpr int EPW = 10;     // envs per warp (lanes 30, 31 idle)
-constexpr int MAXCL = 16;   // contacts one lane can own (a bar lying flat on the floor: 14; local memory, cached as used)
-constexpr int KHAND = 3;    // bar-bar contacts per bar pair handed to the env's lane 2 per round
-constexpr int MAXH = 12;    // bar-bar contacts one pair can have
+#ifndef TB_KP
+#define TB_KP 1
+#endif
+constexpr int KP = TB_KP;   // contacts per lane held in shared memory; a lane's later contacts live in its part of the
+constexpr int KS = 16;      // env's global spill area (KS slots per lane).  Slot addresses depend on (lane, k) only, so
+constexpr int NCS = 3 * KP; // the order in which contacts are summed never depends on timing.
+constexpr int MAXCL = KP + KS;   // contacts one lane can own (a bar lying flat on the floor: 14)
 constexpr int ZONE_TOP = 0, ZONE_BOTTOM = 1, ZONE_MIDDLE = 2;
 
+// one contact.  Written by its owner lane; read by the lanes of the bars it touches.
 template <typename real>
 struct Con {
   real frame[9];
   real r1[3], r2[3];   // contact point relative to the centre of body 1 / body 2 (world axes)
-  real aref[6], jar[6], jv[6], force[6];
-  real su[6];
-  real D0, wcoef, ca, cb;
-  real U0, V0, UU, UV, VV, q0, q1, q2;
+  real jar[6], jv[6];
+  real wr[6];          // world-frame wrench (force, torque) of the current contact force
+  real D0;
+  union {
+    struct { real bw[6], wcoef, ca, cb; } h;                     // cone state for the Hessian, world frame (eval -> assembly)
+    struct { real U0, V0, UU, UV, VV, q0, q1, q2; } ls;          // line-search coefficients (line search only)
+  } t;
   int b1, b2;          // bar index 0..2, or -1 for the world (b1 only)
-  int zone, pad;
+  int zone, owner;     // owner: lane (bar index) that processes the contact, -1 = empty slot
 };
-
-template <typename real> struct HandCon { real dist, pos[3], nrm[3]; int b1, b2; };
 
 // per-env slice of shared memory
 template <typename real>
 struct EnvSh {
-  // home of the env state between physics calls (always double: the HBM record's precision)
-  double qpos[NQ], qvel[NV], warm[NV], ctrl[NACT], act[NACT];
   // world-frame exchange, rewritten by every pass; xpos / xmat / sph / tlen double as the "stale" kinematics the
   // reference's observation reads (positions lag qpos by one substep)
   real xpos[9], xmat[27], vw[18], sph[18], tlen[NTEN], actdot[NACT];
+  double ctrl[NACT], act[NACT];
   union {
-    real site[NEND * 3];                       // tendon end points (tendon stage)
-    HandCon<real> hand[3][KHAND];              // bar-bar contacts found by the pair lanes (collision stage)
-    struct { real xv[NV], fx[NV], Hg[2 * 21]; } sol;  // solver: vector under J, wrenches of lane-2 contacts, blocks 0/1
-    real cfrc[24];                             // after the last pass
+    struct { double qpos[NQ], qvel[NV], warm[NV]; } home;   // env state between physics calls (HBM record precision)
+    real site[NEND * 3];                                    // tendon end points (tendon stage)
+    struct {                                                // Newton solver
+      real D[3][21];      // diagonal blocks, packed lower; after factorisation unit L below the diagonal, d on it
+      real O[3][36];      // blocks below the diagonal, full 6x6 row-major: pairs (1,0), (2,0), (2,1)
+      real dinv[NV];
+      real xv[NV];        // world-frame twists of the vector under J; during the solve: the block rows' partial solutions
+    } sol;
   } u;
-  int nhand[3];
+  real cfrc[24];          // mj_rnePostConstraint of the last pass
+  Con<real> con[NCS];
+  Con<real>* spill;       // global memory: 3 * KS slots of this env-in-flight
+  int ncl[3];             // contacts owned by each lane
+  int cpl[3];             // which blocks below the diagonal exist (set by the pair owners)
   int nact, overflow, bad, niter, nls, nmpr;
   real barforce;
   // env layer (lane 0 of the env)
@@ -76,8 +92,20 @@ template <typename real> TB_FN real sum3(real v, int base) {
 }
 TB_FN int isum3(int v, int base) { return shfl(v, base) + shfl(v, base + 1) + shfl(v, base + 2); }
 TB_FN bool grp_any(bool p, int base) { return ((ballot(p) >> base) & 7u) != 0; }
+// loop conditions: uniform over the warp, or over the CTA when its warps run aligned (they then share fetched
+// instructions; every warp of the CTA executes the same sequence of these calls)
+TB_FN bool uni_any(bool p, bool aligned) {
+#if TB_DEV
+  if (aligned) return __syncthreads_or(p ? 1 : 0) != 0;
+#endif
+  (void)aligned;
+  return any(p);
+}
 
 template <typename real> struct BarState { real x[3], q[4], v[6], warm[6]; };
+
+// k-th contact of lane `owner`
+template <typename real> TB_FN Con<real>& con_of(EnvSh<real>& S, int owner, int k) { return k < KP ? S.con[owner * KP + k] : S.spill[owner * KS + k - KP]; }
 
 // ------------------------------------------------------------------ contact helpers
 template <typename real> TB_FN void make_frame(real* f) {
@@ -105,13 +133,6 @@ template <typename real> TB_FN void con_mulJ(const Con<real>& c, const real* xv,
   }
   for (int a = 0; a < 3; a++) { out[a] = dot3(c.frame + 3 * a, rel); out[3 + a] = dot3(c.frame + 3 * a, relw); }
 }
-// world wrench (force F, torque T) of the contact force: side 2 receives (F, r2 x F + T), side 1 the opposite about r1
-template <typename real> TB_FN void con_wrench(const Con<real>& c, real* F, real* T) {
-  for (int k = 0; k < 3; k++) {
-    F[k] = c.frame[k] * c.force[0] + c.frame[3 + k] * c.force[1] + c.frame[6 + k] * c.force[2];
-    T[k] = c.frame[k] * c.force[3] + c.frame[3 + k] * c.force[4] + c.frame[6 + k] * c.force[5];
-  }
-}
 template <typename real> TB_FN real impedance(const ModelT<real>& m, real pos) {
   const real MINIMP = real(0.0001), MAXIMP = real(0.9999);
   real d0 = clampr(m.solimp[0], MINIMP, MAXIMP), dw = clampr(m.solimp[1], MINIMP, MAXIMP);
@@ -126,45 +147,62 @@ template <typename real> TB_FN real impedance(const ModelT<real>& m, real pos) {
   else y = (real)(1 - (1 / pow(1 - (double)mid, (double)power - 1)) * pow(1 - (double)x, (double)power));
   return d0 + y * (dw - d0);
 }
-// mj_constraintUpdate for one elliptic contact at c.jar: returns its cost; full: also force, zone, Hessian weights
-template <typename real> TB_FN real con_update(Con<real>& c, const ModelT<real>& m, bool full) {
-  real U[6], T = 0, mu = m.mu;
-  U[0] = c.jar[0] * mu;
-  for (int j = 1; j < 6; j++) { U[j] = c.jar[j] * m.fr[j - 1]; T += U[j] * U[j]; }
-  real N = U[0];
+// mj_constraintUpdate for one elliptic contact at jar (+ jv if addjv): returns its cost; full: also the contact force
+// as a world wrench, the zone and the Hessian weights
+template <typename real> TB_FN real con_update(Con<real>& c, const ModelT<real>& m, bool full, bool addjv) {
+  real ja[6], U[6], T = 0, mu = m.mu;
+  for (int j = 0; j < 6; j++) ja[j] = addjv ? c.jar[j] + c.jv[j] : c.jar[j];
+  U[0] = ja[0] * mu;
+  for (int j = 1; j < 6; j++) { U[j] = ja[j] * m.fr[j - 1]; T += U[j] * U[j]; }
+  real N = U[0], f[6];
   T = tsqrt(T);
+  real cost;
   if (N >= mu * T || (T <= 0 && N >= 0)) {
-    if (full) { for (int j = 0; j < 6; j++) c.force[j] = 0; c.zone = ZONE_TOP; c.wcoef = c.ca = c.cb = 0; }
-    return 0;
-  }
-  if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+    if (!full) return 0;
+    for (int j = 0; j < 6; j++) f[j] = 0;
+    c.zone = ZONE_TOP; c.t.h.wcoef = c.t.h.ca = c.t.h.cb = 0;
+    cost = 0;
+  } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
     real s = 0;
     for (int j = 0; j < 6; j++) {
       real D = c.D0 * m.dscale[j];
-      s += real(0.5) * D * c.jar[j] * c.jar[j];
-      if (full) c.force[j] = -D * c.jar[j];
+      s += real(0.5) * D * ja[j] * ja[j];
+      f[j] = -D * ja[j];
     }
-    if (full) { c.zone = ZONE_BOTTOM; c.wcoef = c.D0; c.ca = c.cb = 0; }
-    return s;
-  }
-  real Dm = c.D0 * m.inv_mu2, NT = N - mu * T;
-  if (full) {
+    if (!full) return s;
+    c.zone = ZONE_BOTTOM; c.t.h.wcoef = c.D0; c.t.h.ca = c.t.h.cb = 0;
+    cost = s;
+  } else {
+    real Dm = c.D0 * m.inv_mu2, NT = N - mu * T;
+    cost = real(0.5) * Dm * NT * NT;
+    if (!full) return cost;
     real invT = trcp(T);
-    c.force[0] = -Dm * NT * mu;
+    f[0] = -Dm * NT * mu;
     real kap = mu * mu - mu * N * invT;
-    c.su[0] = 0;
+    real su[6];
+    su[0] = 0;
     for (int j = 1; j < 6; j++) {
-      c.force[j] = -c.force[0] * invT * U[j] * m.fr[j - 1];
-      c.su[j] = m.fr[j - 1] * U[j] * invT;
+      f[j] = -f[0] * invT * U[j] * m.fr[j - 1];
+      su[j] = m.fr[j - 1] * U[j] * invT;
     }
-    c.ca = Dm; c.cb = Dm * kap; c.wcoef = c.cb; c.zone = ZONE_MIDDLE;
+    // b = sum_j su_j J_j as a world-frame 6-vector (linear part from the tangents, angular part from all three axes)
+    for (int k = 0; k < 3; k++) {
+      c.t.h.bw[k] = c.frame[3 + k] * su[1] + c.frame[6 + k] * su[2];
+      c.t.h.bw[3 + k] = c.frame[k] * su[3] + c.frame[3 + k] * su[4] + c.frame[6 + k] * su[5];
+    }
+    c.t.h.ca = Dm; c.t.h.cb = Dm * kap; c.t.h.wcoef = c.t.h.cb; c.zone = ZONE_MIDDLE;
   }
-  return real(0.5) * Dm * NT * NT;
+  for (int k = 0; k < 3; k++) {
+    c.wr[k] = c.frame[k] * f[0] + c.frame[3 + k] * f[1] + c.frame[6 + k] * f[2];
+    c.wr[3 + k] = c.frame[k] * f[3] + c.frame[3 + k] * f[4] + c.frame[6 + k] * f[5];
+  }
+  return cost;
 }
 // cost and its first two derivatives along the search direction at step a, for one contact
 template <typename real> TB_FN void con_ls(const Con<real>& k, const ModelT<real>& m, real a, real& cost, real& d0, real& d1) {
   real mu = m.mu;
-  real N = k.U0 + a * k.V0, Tsqr = k.UU + a * (2 * k.UV + a * k.VV);
+  const real U0 = k.t.ls.U0, V0 = k.t.ls.V0, UU = k.t.ls.UU, UV = k.t.ls.UV, VV = k.t.ls.VV;
+  real N = U0 + a * V0, Tsqr = UU + a * (2 * UV + a * VV);
   bool bottom = false;
   if (Tsqr <= 0) { if (N < 0) bottom = true; }
   else {
@@ -173,35 +211,29 @@ template <typename real> TB_FN void con_ls(const Con<real>& k, const ModelT<real
     else if (mu * N + T <= 0) bottom = true;
     else {
       real invT = trcp(T);
-      real N1 = k.V0, T1 = (k.UV + a * k.VV) * invT;
-      real T2 = k.VV * invT - (k.UV + a * k.VV) * T1 * (invT * invT);
+      real N1 = V0, T1 = (UV + a * VV) * invT;
+      real T2 = VV * invT - (UV + a * VV) * T1 * (invT * invT);
       real NT = N - mu * T, Dm = k.D0 * m.inv_mu2;
       cost += real(0.5) * Dm * NT * NT;
       d0 += Dm * NT * (N1 - mu * T1);
       d1 += Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NT * (-mu * T2));
     }
   }
-  if (bottom) { cost += a * a * k.q2 + a * k.q1 + k.q0; d0 += 2 * a * k.q2 + k.q1; d1 += 2 * k.q2; }
+  if (bottom) { cost += a * a * k.t.ls.q2 + a * k.t.ls.q1 + k.t.ls.q0; d0 += 2 * a * k.t.ls.q2 + k.t.ls.q1; d1 += 2 * k.t.ls.q2; }
 }
 
-// rows of one side's 6x6 Jacobian block in the bar's own dof coordinates (lin world, ang body-local):
-// translational row a = (s f_a, s R^T (r x f_a)), rotational row a = (0, s R^T f_a)
-template <typename real> struct SideJ { real lin[3][3], ang[3][3], rot[3][3]; };
-template <typename real> TB_FN void side_rows(const Con<real>& c, real s, const real* r, const real* R, SideJ<real>& J) {
-  for (int a = 0; a < 3; a++) {
-    const real* f = c.frame + 3 * a;
-    real t[3], w[3];
-    cross3(t, r, f);
-    mulMTV(w, R, t);
-    for (int k = 0; k < 3; k++) { J.lin[a][k] = s * f[k]; J.ang[a][k] = s * w[k]; }
-    mulMTV(w, R, f);
-    for (int k = 0; k < 3; k++) J.rot[a][k] = s * w[k];
-  }
-}
-// 6-vector of row r of a side
-template <typename real> TB_FN void side_row6(const SideJ<real>& J, int r, real* j) {
-  if (r < 3) { for (int k = 0; k < 3; k++) { j[k] = J.lin[r][k]; j[3 + k] = J.ang[r][k]; } }
-  else { for (int k = 0; k < 3; k++) { j[k] = 0; j[3 + k] = J.rot[r - 3][k]; } }
+// ---- Hessian of one contact in world-frame coordinates (per bar: linear dofs, world angular dofs).
+// With J = G T (G: the contact frame applied to the relative twist at the contact point, T = [I, -[r]x ; 0, I] per
+// side) a contact contributes T^T K T, K = G^T W G.  Friction is isotropic in the tangent plane (two equal sliding and
+// two equal rolling coefficients), so the diagonal part of W gives K = blockdiag(w1 I + (w0 - w1) n n^T,
+// w4 I + (w3 - w4) n n^T) in closed form, n = contact normal; a middle-zone cone adds the rank-one terms
+// ca a a^T - cb b b^T with b stored in the contact (world frame) and a = mu (n - b_lin, -b_ang).
+template <typename real> struct ConW { real wl0, wl1, wa3, wa4; };
+template <typename real> TB_FN ConW<real> con_weights(const Con<real>& c, const ModelT<real>& m) {
+  const real* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
+  ConW<real> w;
+  w.wl0 = c.t.h.wcoef * wt[0]; w.wl1 = c.t.h.wcoef * wt[1]; w.wa3 = c.t.h.wcoef * wt[3]; w.wa4 = c.t.h.wcoef * wt[4];
+  return w;
 }
 // H (packed lower 6x6) += w j j^T
 template <typename real> TB_FN void rank1_sym(real* H, real w, const real* j) {
@@ -221,37 +253,85 @@ template <typename real> TB_FN void rank1_gen(real* X, real w, const real* a, co
     for (int k = 0; k < 6; k++) X[6 * i + k] += wi * b[k];
   }
 }
-// cone vectors of a middle-zone contact side: bvec = sum_j su_j J_j, avec = mu (J_0 - bvec)
-template <typename real> TB_FN void side_cone(const Con<real>& c, const ModelT<real>& m, const SideJ<real>& J, real* avec, real* bvec) {
-  for (int k = 0; k < 6; k++) bvec[k] = 0;
-  for (int r = 1; r < 6; r++) {
-    real j[6];
-    side_row6(J, r, j);
-    for (int k = 0; k < 6; k++) bvec[k] += c.su[r] * j[k];
-  }
-  real j0[6];
-  side_row6(J, 0, j0);
-  for (int k = 0; k < 6; k++) avec[k] = m.mu * (j0[k] - bvec[k]);
+// cone vectors of a side: u = T^T v = (v_lin, r x v_lin + v_ang) for v = a, b
+template <typename real> TB_FN void cone_side(const Con<real>& c, const ModelT<real>& m, const real* r, real* ua, real* ub) {
+  const real* n = c.frame;
+  real al[3], aa[3], t[3];
+  for (int k = 0; k < 3; k++) { al[k] = m.mu * (n[k] - c.t.h.bw[k]); aa[k] = -m.mu * c.t.h.bw[3 + k]; }
+  cross3(t, r, al);
+  for (int k = 0; k < 3; k++) { ua[k] = al[k]; ua[3 + k] = t[k] + aa[k]; }
+  cross3(t, r, c.t.h.bw);
+  for (int k = 0; k < 3; k++) { ub[k] = c.t.h.bw[k]; ub[3 + k] = t[k] + c.t.h.bw[3 + k]; }
 }
-// diagonal-block contribution of one contact side
-template <typename real> TB_FN void side_hessian(const Con<real>& c, const ModelT<real>& m, const SideJ<real>& J, real* H) {
-  const real* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
-  for (int r = 0; r < 6; r++) {
-    real w = c.wcoef * wt[r];
-    if (w != 0) { real j[6]; side_row6(J, r, j); rank1_sym(H, w, j); }
-  }
+// diagonal block of one side (r = contact point relative to the bar's centre): H (packed lower 6x6) += T^T K T
+template <typename real> TB_FN void side_hessian(const Con<real>& c, const ModelT<real>& m, const real* r, real* H) {
+  const ConW<real> w = con_weights(c, m);
+  const real* n = c.frame;
+  const real dl = w.wl0 - w.wl1, da = w.wa3 - w.wa4;
+  real cv[3];
+  cross3(cv, r, n);
+  const real rr = dot3(r, r);
+  // lin-lin: w1 I + dl n n^T
+  H[0] += w.wl1 + dl * n[0] * n[0]; H[1] += dl * n[1] * n[0]; H[2] += w.wl1 + dl * n[1] * n[1];
+  H[3] += dl * n[2] * n[0]; H[4] += dl * n[2] * n[1]; H[5] += w.wl1 + dl * n[2] * n[2];
+  // ang-lin (rows 3..5, cols 0..2): w1 [r]x + dl c n^T
+  H[6] += dl * cv[0] * n[0];              H[7] += -w.wl1 * r[2] + dl * cv[0] * n[1]; H[8] += w.wl1 * r[1] + dl * cv[0] * n[2];
+  H[10] += w.wl1 * r[2] + dl * cv[1] * n[0]; H[11] += dl * cv[1] * n[1];              H[12] += -w.wl1 * r[0] + dl * cv[1] * n[2];
+  H[15] += -w.wl1 * r[1] + dl * cv[2] * n[0]; H[16] += w.wl1 * r[0] + dl * cv[2] * n[1]; H[17] += dl * cv[2] * n[2];
+  // ang-ang: w1 (|r|^2 I - r r^T) + dl c c^T + w4 I + da n n^T
+  const real dg = w.wl1 * rr + w.wa4;
+  H[9] += dg - w.wl1 * r[0] * r[0] + dl * cv[0] * cv[0] + da * n[0] * n[0];
+  H[13] += -w.wl1 * r[1] * r[0] + dl * cv[1] * cv[0] + da * n[1] * n[0];
+  H[14] += dg - w.wl1 * r[1] * r[1] + dl * cv[1] * cv[1] + da * n[1] * n[1];
+  H[18] += -w.wl1 * r[2] * r[0] + dl * cv[2] * cv[0] + da * n[2] * n[0];
+  H[19] += -w.wl1 * r[2] * r[1] + dl * cv[2] * cv[1] + da * n[2] * n[1];
+  H[20] += dg - w.wl1 * r[2] * r[2] + dl * cv[2] * cv[2] + da * n[2] * n[2];
   if (c.zone == ZONE_MIDDLE) {
-    real a[6], b[6];
-    side_cone(c, m, J, a, b);
-    rank1_sym(H, c.ca, a);
-    rank1_sym(H, -c.cb, b);
+    real ua[6], ub[6];
+    cone_side(c, m, r, ua, ub);
+    rank1_sym(H, c.t.h.ca, ua);
+    rank1_sym(H, -c.t.h.cb, ub);
+  }
+}
+// block between the two bars of a bar-bar contact: X (6x6 row-major, rows = bar with offset rh, cols = bar with rl)
+// += -T_h^T K T_l   (the two sides enter J with opposite signs)
+template <typename real> TB_FN void cross_hessian(const Con<real>& c, const ModelT<real>& m, const real* rh, const real* rl, real* X) {
+  const ConW<real> w = con_weights(c, m);
+  const real* n = c.frame;
+  const real dl = w.wl0 - w.wl1, da = w.wa3 - w.wa4;
+  real ch[3], cl[3];
+  cross3(ch, rh, n); cross3(cl, rl, n);
+  const real hl = dot3(rh, rl);
+  // [r]x as a matrix: rows (0, -z, y), (z, 0, -x), (-y, x, 0)
+  const real Sh[9] = {0, -rh[2], rh[1], rh[2], 0, -rh[0], -rh[1], rh[0], 0};
+  const real Sl[9] = {0, -rl[2], rl[1], rl[2], 0, -rl[0], -rl[1], rl[0], 0};
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) {
+      const real id = i == k ? real(1) : real(0);
+      // lin-lin: A = w1 I + dl n n^T
+      X[6 * i + k] -= w.wl1 * id + dl * n[i] * n[k];
+      // lin(h)-ang(l): A X_l = -w1 [r_l]x + dl n c_l^T
+      X[6 * i + 3 + k] -= -w.wl1 * Sl[3 * i + k] + dl * n[i] * cl[k];
+      // ang(h)-lin(l): X_h^T A = w1 [r_h]x + dl c_h n^T
+      X[6 * (3 + i) + k] -= w.wl1 * Sh[3 * i + k] + dl * ch[i] * n[k];
+      // ang-ang: w1 ((r_h . r_l) I - r_l r_h^T) + dl c_h c_l^T + w4 I + da n n^T
+      X[6 * (3 + i) + 3 + k] -= w.wl1 * (hl * id - rl[i] * rh[k]) + dl * ch[i] * cl[k] + w.wa4 * id + da * n[i] * n[k];
+    }
+  if (c.zone == ZONE_MIDDLE) {
+    real uah[6], ubh[6], ual[6], ubl[6];
+    cone_side(c, m, rh, uah, ubh); cone_side(c, m, rl, ual, ubl);
+    rank1_gen(X, -c.t.h.ca, uah, ual);
+    rank1_gen(X, c.t.h.cb, ubh, ubl);
   }
 }
 
-// ---- 6x6 block kernels of the Newton solve (packed lower triangles: entry (i, k) at i (i + 1) / 2 + k; full blocks
-// row-major).  Everything is unrolled over static indices, so blocks that are plain local variables stay in registers.
+// ---- 6x6 block kernels of the Newton solve on blocks in shared memory (packed lower triangles: entry (i, k) at
+// i (i + 1) / 2 + k; full blocks row-major).  Each loads its operands into registers, works unrolled, stores back.
 // A = L D L^T in place: strict lower part = unit L, diagonal = d; dinv = 1 / d
-template <typename real> TB_FN void blk_ldl(real* A, real* dinv) {
+template <typename real> TB_FN void blk_ldl(real* Ag, real* dinvg) {
+  real A[21], dinv[6];
+  TB_UNROLL
+  for (int e = 0; e < 21; e++) A[e] = Ag[e];
   TB_UNROLL
   for (int j = 0; j < 6; j++) {
     real s = A[j * (j + 1) / 2 + j];
@@ -268,8 +348,12 @@ template <typename real> TB_FN void blk_ldl(real* A, real* dinv) {
     A[j * (j + 1) / 2 + j] = s;
     dinv[j] = trcp(s);
   }
+  TB_UNROLL
+  for (int e = 0; e < 21; e++) Ag[e] = A[e];
+  TB_UNROLL
+  for (int j = 0; j < 6; j++) dinvg[j] = dinv[j];
 }
-template <typename real> TB_FN void blk_fwd(const real* L, real* x) {   // x <- L^-1 x
+template <typename real> TB_FN void blk_fwd(const real* L, real* x) {   // x <- L^-1 x   (x in registers)
   TB_UNROLL
   for (int i = 1; i < 6; i++) {
     real t = x[i];
@@ -287,55 +371,51 @@ template <typename real> TB_FN void blk_bwd(const real* L, real* x) {   // x <- 
     x[i] = t;
   }
 }
-// X <- X L^-T D^-1   (X a full 6x6 block below the diagonal block L D L^T)
-template <typename real> TB_FN void blk_trsm(real* X, const real* L, const real* dinv) {
+// X <- X L^-T D^-1   (X a full 6x6 block below the diagonal block L D L^T), row by row
+template <typename real> TB_FN void blk_trsm(real* Xg, const real* Lg, const real* dinvg) {
+  real L[21], dinv[6];
   TB_UNROLL
+  for (int e = 0; e < 21; e++) L[e] = Lg[e];
+  TB_UNROLL
+  for (int e = 0; e < 6; e++) dinv[e] = dinvg[e];
+  TB_UNROLL1
   for (int r = 0; r < 6; r++) {
     real u[6];
     TB_UNROLL
     for (int k = 0; k < 6; k++) {
-      real t = X[6 * r + k];
+      real t = Xg[6 * r + k];
       TB_UNROLL
       for (int q = 0; q < k; q++) t -= u[q] * L[k * (k + 1) / 2 + q];
       u[k] = t;
     }
     TB_UNROLL
-    for (int k = 0; k < 6; k++) X[6 * r + k] = u[k] * dinv[k];
+    for (int k = 0; k < 6; k++) Xg[6 * r + k] = u[k] * dinv[k];
   }
 }
-// C (packed) -= A diag(d) A^T
-template <typename real> TB_FN void blk_syrk(real* C, const real* A, const real* Ld) {
+// C -= A diag(d) B^T, d = diagonal of the packed block Ld.  sym: C packed lower (A == B), else C full row-major.
+template <typename real> TB_FN void blk_mulsub(real* Cg, const real* Ag, const real* Ldg, const real* Bg, bool sym) {
+  real Bm[36], d[6];
   TB_UNROLL
+  for (int e = 0; e < 36; e++) Bm[e] = Bg[e];
+  TB_UNROLL
+  for (int k = 0; k < 6; k++) d[k] = Ldg[k * (k + 1) / 2 + k];
+  TB_UNROLL1
   for (int i = 0; i < 6; i++) {
     real ad[6];
     TB_UNROLL
-    for (int k = 0; k < 6; k++) ad[k] = A[6 * i + k] * Ld[k * (k + 1) / 2 + k];
-    TB_UNROLL
-    for (int j = 0; j <= i; j++) {
-      real sacc = 0;
-      TB_UNROLL
-      for (int k = 0; k < 6; k++) sacc += ad[k] * A[6 * j + k];
-      C[i * (i + 1) / 2 + j] -= sacc;
-    }
-  }
-}
-// C (full) -= A diag(d) B^T
-template <typename real> TB_FN void blk_gemm(real* C, const real* A, const real* Ld, const real* B) {
-  TB_UNROLL
-  for (int i = 0; i < 6; i++) {
-    real ad[6];
-    TB_UNROLL
-    for (int k = 0; k < 6; k++) ad[k] = A[6 * i + k] * Ld[k * (k + 1) / 2 + k];
+    for (int k = 0; k < 6; k++) ad[k] = Ag[6 * i + k] * d[k];
+    real* Crow = sym ? Cg + i * (i + 1) / 2 : Cg + 6 * i;
     TB_UNROLL
     for (int j = 0; j < 6; j++) {
+      if (sym && j > i) break;
       real sacc = 0;
       TB_UNROLL
-      for (int k = 0; k < 6; k++) sacc += ad[k] * B[6 * j + k];
-      C[6 * i + j] -= sacc;
+      for (int k = 0; k < 6; k++) sacc += ad[k] * Bm[6 * j + k];
+      Crow[j] -= sacc;
     }
   }
 }
-template <typename real> TB_FN void blk_gemv_sub(real* y, const real* A, const real* x) {   // y -= A x
+template <typename real> TB_FN void blk_gemv_sub(real* y, const real* A, const real* x) {   // y -= A x   (y in registers)
   TB_UNROLL
   for (int i = 0; i < 6; i++) {
     real t = y[i];
@@ -413,21 +493,6 @@ template <typename real> TB_FN real ptseg_dist2(const real* c, const real* p, co
   return dot3(r, r);
 }
 
-// appends an active contact to the lane's list (dist >= 0 gives no rows: includemargin 0)
-template <typename real>
-TB_FN void add_contact(Con<real>* con, int& ncon, int& overflow, int b1, int b2, real dist, const real* pos, const real* normal,
-                       const real* xpos) {
-  if (!(dist < 0)) return;
-  if (ncon >= MAXCL) { overflow = 1; return; }
-  Con<real>& c = con[ncon++];
-  c.b1 = b1; c.b2 = b2;
-  copy3(c.frame, normal);
-  make_frame(c.frame);
-  sub3(c.r2, pos, xpos + 3 * b2);
-  if (b1 >= 0) sub3(c.r1, pos, xpos + 3 * b1); else { c.r1[0] = c.r1[1] = c.r1[2] = 0; }
-  c.aref[0] = dist;   // parked until the rows are built
-}
-
 // height-field prism k of row r (vertices n = k, k+1, k+2 of the strip; c = cmin + n/2, odd n -> row r, even -> r + 1)
 template <typename real> TB_FN void hf_prism(const ModelT<real>& m, int r, int cmin, int k, CObj<real>& o) {
   for (int j = 0; j < 3; j++) {
@@ -459,14 +524,29 @@ TB_FN bool hf_above_top_plane(const CObj<real>& pr, int gtype, const real* pos, 
   return sep > real(1e-9) * tsqrt(nn);
 }
 
+// stores a new active contact of this lane (dist >= 0 gives no rows: includemargin 0)
+template <typename real>
+TB_FN void add_contact(EnvSh<real>& S, int lane_bar, int& nmine, int b1, int b2, real dist, const real* pos, const real* normal) {
+  if (!(dist < 0)) return;
+  if (nmine >= MAXCL) { S.overflow = 1; return; }
+  Con<real>& c = con_of(S, lane_bar, nmine++);
+  c.b1 = b1; c.b2 = b2; c.owner = lane_bar;
+  copy3(c.frame, normal);
+  make_frame(c.frame);
+  sub3(c.r2, pos, S.xpos + 3 * b2);
+  if (b1 >= 0) sub3(c.r1, pos, S.xpos + 3 * b1); else { c.r1[0] = c.r1[1] = c.r1[2] = 0; }
+  c.D0 = dist;   // parked until the rows are built
+}
+
 // ------------------------------------------------------------------ one physics pass
 // mj_forward (integ = false) or mj_step (integ = true) for the envs of the warp that are `on`.  The bar state B is
-// the lane's registers; con / ncon (lane-local) hold the contacts of the last pass on return.
+// the lane's registers; the env's contacts of the last pass stay in S on return.
 template <typename real>
-TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, bool integ,
-                Con<real>* con, int& ncon) {
+TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, bool integ, bool aligned) {
   const int b = L.bar, base = L.base;
   const real MINV = Lim<real>::MINVAL;
+  const real* Mb = m.M + 6 * b;
+  real* const qacc = B.warm;   // the acceleration iterate starts from (and ends as) the warm start
   auto reset_data = [&]() {   // mj_resetData on this lane's bar
     for (int k = 0; k < 3; k++) B.x[k] = m.qpos0[7 * b + k];
     for (int k = 0; k < 4; k++) B.q[k] = m.qpos0[7 * b + 3 + k];
@@ -482,8 +562,9 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     if (bad && on) { if (b == 0) S.bad |= 1; reset_data(); }
     wsync();
   }
-  real R[9], fsm[6], asm_[6], Dblk[21], qacc[6], fcon[6];
+  real R[9], asm_[6], Dblk[21], fcon[6], Iw[6];
   bool pass_on = on;
+  TB_UNROLL1
   for (int pass = 0; pass < 2; pass++) {
   // ---------------- position stage
   if (pass_on) {
@@ -552,21 +633,39 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       for (int k = 0; k < 6; k++) f[k] += sg * j[k];
       rank1_sym(Dblk, Bt, j);
     }
-    // qfrc_smooth = passive + actuator - bias ; qacc_smooth = M^-1 qfrc_smooth
+    // qacc_smooth = M^-1 (passive + actuator - bias)
     const real* I = m.inertia[b];
     const real* w = B.v + 3;
+    real al[3];
     for (int k = 0; k < 3; k++) {
-      fsm[k] = f[k] + m.M[6 * b + k] * m.grav[k];
       int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-      fsm[3 + k] = f[3 + k] - (w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]));
+      asm_[k] = (f[k] + Mb[k] * m.grav[k]) * m.invM[6 * b + k];
+      al[k] = (f[3 + k] - (w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]))) * m.invM[6 * b + 3 + k];
     }
-    for (int k = 0; k < 6; k++) asm_[k] = fsm[k] * m.invM[6 * b + k];
+    // from here to the end of the solve the bar's angular dofs are WORLD-frame components (the rotation is orthogonal,
+    // so costs, norms and the Newton direction are the same as in body coordinates): qacc_smooth, the warm start /
+    // iterate, and the rotational inertia R diag(I) R^T
+    mulMV(asm_ + 3, R, al);
+    mulMV(al, R, B.warm + 3);
+    for (int k = 0; k < 3; k++) B.warm[3 + k] = al[k];
+    for (int i = 0, e = 0; i < 3; i++)
+      for (int k = 0; k <= i; k++, e++) Iw[e] = R[3 * i] * I[0] * R[3 * k] + R[3 * i + 1] * I[1] * R[3 * k + 1] + R[3 * i + 2] * I[2] * R[3 * k + 2];
   }
-  wsync();   // the tendon end points are dead: the union now carries the bar-bar hand-off
+  wsync();   // the tendon end points are dead: their storage now carries the solver's exchange
+  // publishes a per-bar 6-vector (a world-frame twist) for the contact owners
+  auto publish = [&](const real* a, bool doit) {
+    if (doit) for (int k = 0; k < 6; k++) S.u.sol.xv[6 * b + k] = a[k];
+  };
+  // out = M_w d for this bar (mass on the linear part, world-frame rotational inertia on the angular part)
+  auto mulM = [&](const real* d, real* out) {
+    for (int k = 0; k < 3; k++) out[k] = Mb[k] * d[k];
+    out[3] = Iw[0] * d[3] + Iw[1] * d[4] + Iw[3] * d[5];
+    out[4] = Iw[1] * d[3] + Iw[2] * d[4] + Iw[4] * d[5];
+    out[5] = Iw[3] * d[3] + Iw[4] * d[4] + Iw[5] * d[5];
+  };
+  publish(asm_, pass_on);
   // ---------------- collision
-  if (pass_on) ncon = 0;
-  int overflow = 0, nmpr = 0, nh = 0;
-  HandCon<real> found[MAXH];   // bar-bar contacts of this lane's pair
+  int nmine = 0, nmpr = 0;
   if (pass_on) {
     if (m.floor_type == 0) {
       TB_UNROLL1
@@ -581,13 +680,13 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
           if (cdist <= r) {
             real dist = cdist - r, pos[3];
             copy3(pos, c); addscl3(pos, m.fnormal, -dist / 2 - r);
-            add_contact(con, ncon, overflow, -1, b, dist, pos, m.fnormal, S.xpos);
+            add_contact(S, b, nmine, -1, b, dist, pos, m.fnormal);
           }
         } else if (cdist <= m.gbound[Gi]) {
           real axis[3] = {R[2], R[5], R[8]}, xaxis[3] = {R[0], R[3], R[6]}, dist[4], pts[4][3];
           int cnt = 0;
           plane_cylinder_points(m, c, axis, m.gsize[Gi][0], m.gsize[Gi][1], xaxis, cnt, dist, pts);
-          for (int k = 0; k < cnt; k++) add_contact(con, ncon, overflow, -1, b, dist[k], pts[k], m.fnormal, S.xpos);
+          for (int k = 0; k < cnt; k++) add_contact(S, b, nmine, -1, b, dist[k], pts[k], m.fnormal);
         }
       }
     } else {
@@ -645,7 +744,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
                 real nn[3]; sub3(nn, gc, cp);
                 if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(dir, nn); }
               }
-              add_contact(con, ncon, overflow, -1, b, -depth, cp, dir, S.xpos);
+              add_contact(S, b, nmine, -1, b, -depth, cp, dir);
             }
           }
         }
@@ -656,7 +755,6 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     {
       const int p = b, pb1 = p == 2 ? 1 : 0, pb2 = p == 0 ? 1 : 2;
       const real *X1 = S.xpos + 3 * pb1, *X2 = S.xpos + 3 * pb2, *R1 = S.xmat + 9 * pb1, *R2 = S.xmat + 9 * pb2;
-      // bar-level cull: the bars' bounding capsules (axis segment of the whole bar, largest radius)
       TB_UNROLL1
       for (int i = 0; i < 25; i++) {
         int g1 = 5 * pb1 + i / 5, g2 = 5 * pb2 + i % 5;
@@ -707,139 +805,107 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
             if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(nrm, nn); }
           }
         }
-        if (hit && dist < 0) {
-          if (nh < MAXH) {
-            HandCon<real>& hc = found[nh++];
-            hc.dist = dist; copy3(hc.pos, pos); copy3(hc.nrm, nrm); hc.b1 = cb1; hc.b2 = cb2;
-          } else overflow = 1;
-        }
+        if (hit) add_contact(S, b, nmine, cb1, cb2, dist, pos, nrm);
       }
     }
   }
-  // hand-off to lane 2, KHAND contacts per pair and round (one round unless a pair has more than KHAND contacts)
-  bool coupled = false;   // does this env have a bar-bar contact (lane 2 owns them)
-  TB_UNROLL1
-  for (int round = 0;; round++) {
-    const int lo = round * KHAND;
-    if (pass_on) {
-      int cnt = nh - lo; cnt = cnt < 0 ? 0 : (cnt > KHAND ? KHAND : cnt);
-      for (int k = 0; k < cnt; k++) S.u.hand[b][k] = found[lo + k];
-      S.nhand[b] = cnt;
-    }
-    wsync();
-    if (pass_on && b == 2) {
-      for (int p = 0; p < 3; p++)
-        for (int k = 0; k < S.nhand[p]; k++) {
-          const HandCon<real>& hc = S.u.hand[p][k];
-          add_contact(con, ncon, overflow, hc.b1, hc.b2, hc.dist, hc.pos, hc.nrm, S.xpos);
-          coupled = true;
-        }
-    }
-    if (!any(pass_on && nh > lo + KHAND)) break;
-    wsync();
-  }
-  coupled = grp_any(coupled, base);
-  {
-    int nact = isum3(pass_on ? ncon : 0, base), ov = isum3(pass_on ? overflow : 0, base), nm = isum3(pass_on ? nmpr : 0, base);
-    if (pass_on && b == 0) { S.nact = nact; if (ov) S.overflow = 1; S.nmpr += nm; }
-  }
-  // rows: velocity, impedance, reference acceleration
-  if (pass_on) {
+  if (pass_on) S.ncl[b] = nmine;
+  wsync();
+  // rows of this lane's contacts: velocity, impedance, reference acceleration, residual at qacc_smooth
+  real csm = 0;
+  bool bbmine = false;   // does this lane own a bar-bar contact
+  if (pass_on && nmine > 0) {
     TB_UNROLL1
-    for (int n = 0; n < ncon; n++) {
-      Con<real>& c = con[n];
-      real dist = c.aref[0], vel[6];
+    for (int s = 0; s < nmine; s++) {
+      Con<real>& c = con_of(S, b, s);
+      real dist = c.D0, vel[6], ja[6];
       con_mulJ(c, S.vw, vel);
+      con_mulJ(c, S.u.sol.xv, ja);
       real imp = impedance(m, dist);
       real tran = (c.b1 >= 0 ? m.invw_tran[c.b1] : real(0)) + m.invw_tran[c.b2];
       c.D0 = trcp(tmax(MINV, tdiv(1 - imp, imp) * tran));
-      for (int r = 0; r < 6; r++) c.aref[r] = -m.B * vel[r] - (r ? real(0) : m.K * imp * dist);
+      for (int r = 0; r < 6; r++) c.jar[r] = ja[r] - (-m.B * vel[r] - (r ? real(0) : m.K * imp * dist));
+      csm += con_update(c, m, false, false);
+      if (c.b1 >= 0) bbmine = true;
     }
   }
-  wsync();   // the hand-off slots are dead: the union now carries the solver exchange
+  const bool coupled = grp_any(pass_on && bbmine, base);   // does this env have a bar-bar contact
+  const int nact_env = isum3(pass_on ? nmine : 0, base);
+  {
+    int nm = isum3(pass_on ? nmpr : 0, base);
+    if (pass_on && b == 0) { S.nact = nact_env; S.nmpr += nm; }
+  }
   // ---------------- mj_fwdConstraint: warm-start choice + Newton
-  const int nact_env = isum3(pass_on ? ncon : 0, base);
   bool act = pass_on && nact_env > 0;
-  const real* Mb = m.M + 6 * b;
-  // publishes a per-bar 6-vector (lin world, ang body-local) as a world-frame twist
-  auto publish = [&](const real* a, bool doit) {
-    if (doit) {
-      real w[3];
-      mulMV(w, R, a + 3);
-      for (int k = 0; k < 3; k++) { S.u.sol.xv[6 * b + k] = a[k]; S.u.sol.xv[6 * b + 3 + k] = w[k]; }
-    }
-  };
-  auto jar_from_xv = [&]() {
-    TB_UNROLL1
-    for (int n = 0; n < ncon; n++) {
-      real o[6];
-      con_mulJ(con[n], S.u.sol.xv, o);
-      for (int r = 0; r < 6; r++) con[n].jar[r] = o[r] - con[n].aref[r];
-    }
-  };
-  auto cost_only = [&](const real* a) -> real {   // this lane's share of the cost at a (jar current)
-    real s = 0;
-    TB_UNROLL1
-    for (int n = 0; n < ncon; n++) s += con_update(con[n], m, false);
-    for (int k = 0; k < 6; k++) { real d = a[k] - asm_[k]; s += real(0.5) * Mb[k] * d * d; }
-    return s;
-  };
   bool use_smooth = false;
-  if (any(act)) {
-    publish(asm_, act); wsync();
-    real csm = 0, cws = 0;
-    if (act) { jar_from_xv(); csm = cost_only(asm_); }
+  if (uni_any(act, aligned)) {
     wsync();
-    publish(B.warm, act); wsync();
-    if (act) { jar_from_xv(); cws = cost_only(B.warm); }
+    real dw[6];
+    for (int k = 0; k < 6; k++) dw[k] = B.warm[k] - asm_[k];
+    publish(dw, act);
+    wsync();
+    real cws = 0;
+    if (act) {
+      if (nmine > 0) {
+        TB_UNROLL1
+        for (int s = 0; s < nmine; s++) {
+          Con<real>& c = con_of(S, b, s);
+          con_mulJ(c, S.u.sol.xv, c.jv);
+          cws += con_update(c, m, false, true);
+        }
+      }
+      real md[6];
+      mulM(dw, md);
+      for (int k = 0; k < 6; k++) cws += real(0.5) * md[k] * dw[k];
+    }
     csm = sum3(csm, base); cws = sum3(cws, base);
     use_smooth = cws > csm;
-    wsync();
-    if (any(act && use_smooth)) {
-      publish(asm_, act && use_smooth); wsync();
-      if (act && use_smooth) jar_from_xv();
-      wsync();
+    if (act && !use_smooth && nmine > 0) {
+      TB_UNROLL1
+      for (int s = 0; s < nmine; s++) {
+        Con<real>& c = con_of(S, b, s);
+        for (int r = 0; r < 6; r++) c.jar[r] += c.jv[r];
+      }
     }
   }
-  for (int k = 0; k < 6; k++) { qacc[k] = (act && !use_smooth) ? B.warm[k] : asm_[k]; fcon[k] = 0; }
+  if (pass_on) { if (!act || use_smooth) for (int k = 0; k < 6; k++) qacc[k] = asm_[k]; }
+  for (int k = 0; k < 6; k++) fcon[k] = 0;
   real grad[6], search[6] = {0, 0, 0, 0, 0, 0};
   real cost = 0, oldcost = 0;
   int iter = 0, nls = 0;
   bool first = true;
   TB_UNROLL1
   for (;;) {
-    if (!any(act)) break;
-    // ---- cost, forces, gradient at qacc
-    real cpart = 0, Fw[3] = {0, 0, 0}, Tw[3] = {0, 0, 0};
-    if (act && coupled) for (int k = 0; k < 6; k++) S.u.sol.fx[6 * b + k] = 0;
-    if (any(act && coupled)) wsync();
-    if (act) {
+    if (!uni_any(act, aligned)) break;
+    // ---- forces at qacc (owners), then each bar lane gathers the wrenches of the contacts that touch its bar
+    real cpart = 0;
+    if (act && nmine > 0) {
       TB_UNROLL1
-      for (int n = 0; n < ncon; n++) {
-        Con<real>& c = con[n];
-        cpart += con_update(c, m, true);
-        if (c.zone == ZONE_TOP) continue;
-        real F[3], T[3], t[3];
-        con_wrench(c, F, T);
-        cross3(t, c.r2, F);
-        if (c.b1 < 0) { for (int k = 0; k < 3; k++) { Fw[k] += F[k]; Tw[k] += t[k] + T[k]; } }
-        else {   // bar-bar (this is lane 2): through shared memory to the two bars' lanes
-          real* f2 = S.u.sol.fx + 6 * c.b2; real* f1 = S.u.sol.fx + 6 * c.b1;
-          for (int k = 0; k < 3; k++) { f2[k] += F[k]; f2[3 + k] += t[k] + T[k]; }
-          cross3(t, c.r1, F);
-          for (int k = 0; k < 3; k++) { f1[k] -= F[k]; f1[3 + k] -= t[k] + T[k]; }
-        }
+      for (int s = 0; s < nmine; s++) {
+        Con<real>& c = con_of(S, b, s);
+        cpart += con_update(c, m, true, false);
       }
-      for (int k = 0; k < 6; k++) { real d = qacc[k] - asm_[k]; cpart += real(0.5) * Mb[k] * d * d; }
     }
-    if (any(act && coupled)) wsync();
+    wsync();
     real gn = 0;
     if (act) {
-      if (coupled) for (int k = 0; k < 3; k++) { Fw[k] += S.u.sol.fx[6 * b + k]; Tw[k] += S.u.sol.fx[6 * b + 3 + k]; }
-      real tl[3];
-      mulMTV(tl, R, Tw);
-      for (int k = 0; k < 3; k++) { fcon[k] = Fw[k]; fcon[3 + k] = tl[k]; }
-      for (int k = 0; k < 6; k++) { grad[k] = Mb[k] * (qacc[k] - asm_[k]) - fcon[k]; gn += grad[k] * grad[k]; }
+      real Fw[3] = {0, 0, 0}, Tw[3] = {0, 0, 0};
+      TB_UNROLL1
+      for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
+        const Con<real>& c = con_of(S, o, s);
+        if (c.zone == ZONE_TOP) continue;
+        real t[3];
+        if (c.b2 == b) { cross3(t, c.r2, c.wr); for (int k = 0; k < 3; k++) { Fw[k] += c.wr[k]; Tw[k] += t[k] + c.wr[3 + k]; } }
+        else if (c.b1 == b) { cross3(t, c.r1, c.wr); for (int k = 0; k < 3; k++) { Fw[k] -= c.wr[k]; Tw[k] -= t[k] + c.wr[3 + k]; } }
+      }
+      for (int k = 0; k < 3; k++) { fcon[k] = Fw[k]; fcon[3 + k] = Tw[k]; }
+      real d[6], md[6];
+      for (int k = 0; k < 6; k++) d[k] = qacc[k] - asm_[k];
+      mulM(d, md);
+      for (int k = 0; k < 6; k++) {
+        cpart += real(0.5) * md[k] * d[k];
+        grad[k] = md[k] - fcon[k]; gn += grad[k] * grad[k];
+      }
     }
     real newcost = sum3(cpart, base);
     gn = sum3(gn, base);
@@ -850,122 +916,121 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     first = false;
     const bool go = act && iter < m.iterations;
     if (!go) act = false;
-    if (!any(go)) break;
-    // ---- Hessian blocks
-    real H[21];
+    if (!uni_any(go, aligned)) break;
+    // ---- Hessian: every bar lane builds its diagonal block from the contacts touching its bar, the owner of a
+    // bar-bar contact the block below the diagonal; all into shared memory
     if (go) {
-      for (int i = 0, e = 0; i < 6; i++) for (int k = 0; k <= i; k++, e++) H[e] = (i == k) ? Mb[i] : real(0);
+      real H[21];
+      for (int e = 0; e < 21; e++) H[e] = 0;
+      H[0] = H[2] = H[5] = Mb[0];
+      H[9] = Iw[0]; H[13] = Iw[1]; H[14] = Iw[2]; H[18] = Iw[3]; H[19] = Iw[4]; H[20] = Iw[5];
+      S.cpl[b] = 0;
       TB_UNROLL1
-      for (int n = 0; n < ncon; n++) {
-        const Con<real>& c = con[n];
-        if (c.zone == ZONE_TOP || c.b1 >= 0) continue;
-        SideJ<real> J;
-        side_rows(c, real(1), c.r2, R, J);
-        side_hessian(c, m, J, H);
+      for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
+        const Con<real>& c = con_of(S, o, s);
+        if (c.zone == ZONE_TOP) continue;
+        if (c.b2 != b && c.b1 != b) continue;
+        side_hessian(c, m, c.b2 == b ? c.r2 : c.r1, H);
       }
-    }
-    if (any(go && coupled)) {
-      // coupled env: lanes 0, 1 hand their diagonal block and gradient to lane 2, which adds the bar-bar contacts'
-      // blocks, factorises the 18x18 system (structural zeros skipped) and returns the search direction
-      if (go && coupled) {
-        if (b < 2) for (int e = 0; e < 21; e++) S.u.sol.Hg[21 * b + e] = H[e];
-        for (int k = 0; k < 6; k++) S.u.sol.fx[6 * b + k] = grad[k];
-      }
-      wsync();
-      if (go && coupled && b == 2) {
-        // blocks: D[bar] (packed, 21 each), then O[pair] (full 6x6: rows = the higher bar, cols = the lower one) for the
-        // pairs (1,0), (2,0), (2,1)
-        real Hb[3 * 21 + 3 * 36];
-        real* const Dg = Hb; real* const Og = Hb + 63;
-        bool cpl[3] = {false, false, false};
-        for (int e = 0; e < 42; e++) Dg[e] = S.u.sol.Hg[e];
-        for (int e = 0; e < 21; e++) Dg[42 + e] = H[e];
+      for (int e = 0; e < 21; e++) S.u.sol.D[b][e] = H[e];
+      if (bbmine) {
+        // this lane owns the pair p = b: rows = the higher bar, cols = the lower one
+        real X[36];
+        for (int e = 0; e < 36; e++) X[e] = 0;
+        bool anyx = false;
         TB_UNROLL1
-        for (int n = 0; n < ncon; n++) {
-          const Con<real>& c = con[n];
-          if (c.zone == ZONE_TOP || c.b1 < 0) continue;
-          SideJ<real> J1, J2;
-          side_rows(c, real(-1), c.r1, S.xmat + 9 * c.b1, J1);
-          side_rows(c, real(1), c.r2, S.xmat + 9 * c.b2, J2);
-          const int hi = c.b1 > c.b2 ? c.b1 : c.b2, lo = c.b1 > c.b2 ? c.b2 : c.b1, p = hi == 1 ? 0 : (lo == 0 ? 1 : 2);
-          real* X = Og + 36 * p;
-          if (!cpl[p]) { for (int e = 0; e < 36; e++) X[e] = 0; cpl[p] = true; }
-          side_hessian(c, m, J1, Dg + 21 * c.b1);
-          side_hessian(c, m, J2, Dg + 21 * c.b2);
-          const SideJ<real>& Jh = c.b2 > c.b1 ? J2 : J1;   // rows: the higher bar
-          const SideJ<real>& Jl = c.b2 > c.b1 ? J1 : J2;
-          const real* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
-          for (int r = 0; r < 6; r++) {
-            real w = c.wcoef * wt[r];
-            if (w != 0) { real jh[6], jl[6]; side_row6(Jh, r, jh); side_row6(Jl, r, jl); rank1_gen(X, w, jh, jl); }
-          }
-          if (c.zone == ZONE_MIDDLE) {
-            real ah[6], bh[6], al[6], bl[6];
-            side_cone(c, m, Jh, ah, bh); side_cone(c, m, Jl, al, bl);
-            rank1_gen(X, c.ca, ah, al);
-            rank1_gen(X, -c.cb, bh, bl);
-          }
+        for (int s = 0; s < nmine; s++) {
+          const Con<real>& c = con_of(S, b, s);
+          if (c.b1 < 0 || c.zone == ZONE_TOP) continue;
+          if (c.b2 > c.b1) cross_hessian(c, m, c.r2, c.r1, X); else cross_hessian(c, m, c.r1, c.r2, X);
+          anyx = true;
         }
-        // block LDL^T in the order 0, 1, 2; structurally absent blocks are skipped (fill-in only in pair (2,1))
-        real dinv[NV], x[NV];
-        for (int i = 0; i < NV; i++) x[i] = S.u.sol.fx[i];
-        real *D0 = Dg, *D1 = Dg + 21, *D2 = Dg + 42, *O10 = Og, *O20 = Og + 36, *O21 = Og + 72;
-        blk_ldl(D0, dinv);
-        if (cpl[0]) { blk_trsm(O10, D0, dinv); blk_syrk(D1, O10, D0); }
-        if (cpl[1]) { blk_trsm(O20, D0, dinv); blk_syrk(D2, O20, D0); }
-        if (cpl[0] && cpl[1]) {
-          if (!cpl[2]) { for (int e = 0; e < 36; e++) O21[e] = 0; cpl[2] = true; }
-          blk_gemm(O21, O20, D0, O10);
-        }
-        blk_ldl(D1, dinv + 6);
-        if (cpl[2]) { blk_trsm(O21, D1, dinv + 6); blk_syrk(D2, O21, D1); }
-        blk_ldl(D2, dinv + 12);
-        blk_fwd(D0, x);
-        if (cpl[0]) blk_gemv_sub(x + 6, O10, x);
-        blk_fwd(D1, x + 6);
-        if (cpl[1]) blk_gemv_sub(x + 12, O20, x);
-        if (cpl[2]) blk_gemv_sub(x + 12, O21, x + 6);
-        blk_fwd(D2, x + 12);
-        for (int i = 0; i < NV; i++) x[i] *= dinv[i];
-        blk_bwd(D2, x + 12);
-        if (cpl[2]) blk_gemvT_sub(x + 6, O21, x + 12);
-        blk_bwd(D1, x + 6);
-        if (cpl[0]) blk_gemvT_sub(x, O10, x + 6);
-        if (cpl[1]) blk_gemvT_sub(x, O20, x + 12);
-        blk_bwd(D0, x);
-        for (int i = 0; i < NV; i++) S.u.sol.xv[i] = -x[i];
+        if (anyx) { for (int e = 0; e < 36; e++) S.u.sol.O[b][e] = X[e]; S.cpl[b] = 1; }
       }
-      wsync();
-      if (go && coupled) for (int k = 0; k < 6; k++) search[k] = S.u.sol.xv[6 * b + k];
-      wsync();
     }
-    if (go && !coupled) {   // this bar's own 6x6 block: LDL^T and solve in registers
-      real dinv[6], x[6];
+    wsync();
+    // ---- block LDL^T in the order bar 0, 1, 2, distributed by block row (lane b owns D[b] and the blocks left of it);
+    // absent blocks are skipped; fill-in can only appear in pair (2,1)
+    {
+      const bool c10 = go && S.cpl[0] != 0, c20 = go && S.cpl[1] != 0, c21in = go && S.cpl[2] != 0;
+      const bool f21 = c10 && c20, c21 = c21in || f21;
+      real (*D)[21] = S.u.sol.D; real (*O)[36] = S.u.sol.O; real* dinv = S.u.sol.dinv; real* xs = S.u.sol.xv;
+      const bool indep = go && (b == 0 || (b == 1 && !c10) || (b == 2 && !c20 && !c21));   // no block left of the diagonal
+      const bool alone = indep && ((b == 0 && !c10 && !c20) || (b == 1 && !c21) || b == 2);   // and none below it
+      real x[6];
       for (int k = 0; k < 6; k++) x[k] = grad[k];
-      blk_ldl(H, dinv);
-      blk_fwd(H, x);
-      for (int k = 0; k < 6; k++) x[k] *= dinv[k];
-      blk_bwd(H, x);
-      for (int k = 0; k < 6; k++) search[k] = -x[k];
+      if (indep) { blk_ldl(D[b], dinv + 6 * b); blk_fwd(D[b], x); }
+      if (alone) { for (int k = 0; k < 6; k++) x[k] *= dinv[6 * b + k]; blk_bwd(D[b], x); }
+      if (uni_any(go && (c10 || c20 || c21), aligned)) {
+        if (go && b == 0 && !alone) for (int k = 0; k < 6; k++) xs[k] = x[k];   // z0
+        wsync();
+        if ((b == 1 && c10) || (b == 2 && c20)) blk_trsm(O[b - 1], D[0], dinv);
+        wsync();
+        if ((b == 1 && c10) || (b == 2 && c20)) blk_mulsub(D[b], O[b - 1], D[0], O[b - 1], true);
+        if (b == 0 && f21) {
+          if (!c21in) for (int e = 0; e < 36; e++) O[2][e] = 0;
+          blk_mulsub(O[2], O[1], D[0], O[0], false);
+        }
+        wsync();
+        if (b == 1 && c10) {
+          blk_ldl(D[1], dinv + 6);
+          blk_gemv_sub(x, O[0], xs);
+          blk_fwd(D[1], x);
+        }
+        if (go && b == 1 && !alone) for (int k = 0; k < 6; k++) xs[6 + k] = x[k];   // z1
+        wsync();
+        if (b == 2 && (c20 || c21)) {
+          if (c21) { blk_trsm(O[2], D[1], dinv + 6); blk_mulsub(D[2], O[2], D[1], O[2], true); }
+          blk_ldl(D[2], dinv + 12);
+          if (c20) blk_gemv_sub(x, O[1], xs);
+          if (c21) blk_gemv_sub(x, O[2], xs + 6);
+          blk_fwd(D[2], x);
+          for (int k = 0; k < 6; k++) x[k] *= dinv[12 + k];
+          blk_bwd(D[2], x);
+          for (int k = 0; k < 6; k++) xs[12 + k] = x[k];   // final x2
+        }
+        wsync();
+        if (go && b == 1 && !alone) {
+          for (int k = 0; k < 6; k++) x[k] *= dinv[6 + k];
+          if (c21) blk_gemvT_sub(x, O[2], xs + 12);
+          blk_bwd(D[1], x);
+          for (int k = 0; k < 6; k++) xs[6 + k] = x[k];   // final x1
+        }
+        wsync();
+        if (go && b == 0 && !alone) {
+          for (int k = 0; k < 6; k++) x[k] *= dinv[k];
+          if (c10) blk_gemvT_sub(x, O[0], xs + 6);
+          if (c20) blk_gemvT_sub(x, O[1], xs + 12);
+          blk_bwd(D[0], x);
+        }
+      }
+      if (go) for (int k = 0; k < 6; k++) search[k] = -x[k];
     }
     // ---- exact line search along search: mj_solPrimal's bracketing search as a per-env state machine.  Every tick
     // evaluates cost / slope / curvature at ONE step size per env (3-lane sums), then each env advances its own
     // bracketing logic, so the envs of a warp stay in lock step whatever their individual search sequences are.
     real snorm = 0, gs = 0, qG1 = 0, qG2 = 0, gauss = 0;
-    if (go) for (int k = 0; k < 6; k++) {
-      real sk = search[k], d = qacc[k] - asm_[k];
-      snorm += sk * sk; gs += grad[k] * sk;
-      qG1 += sk * (Mb[k] * qacc[k]) - fsm[k] * sk;
-      qG2 += real(0.5) * sk * (Mb[k] * sk);
-      gauss += real(0.5) * Mb[k] * d * d;
+    if (go) {
+      real d[6], md[6], ms[6];
+      for (int k = 0; k < 6; k++) d[k] = qacc[k] - asm_[k];
+      mulM(d, md); mulM(search, ms);
+      for (int k = 0; k < 6; k++) {
+        real sk = search[k];
+        snorm += sk * sk; gs += grad[k] * sk;
+        qG1 += sk * md[k];
+        qG2 += real(0.5) * sk * ms[k];
+        gauss += real(0.5) * md[k] * d[k];
+      }
     }
     snorm = sum3(snorm, base); gs = sum3(gs, base);
     snorm = tsqrt(snorm);
-    publish(search, go); wsync();
-    if (go) {
+    wsync();
+    publish(search, go);
+    wsync();
+    if (go && nmine > 0) {
       TB_UNROLL1
-      for (int n = 0; n < ncon; n++) {
-        Con<real>& k = con[n];
+      for (int s = 0; s < nmine; s++) {
+        Con<real>& k = con_of(S, b, s);
         con_mulJ(k, S.u.sol.xv, k.jv);
         real q0 = 0, q1 = 0, q2 = 0, UU = 0, UV = 0, VV = 0;
         for (int j = 0; j < 6; j++) {
@@ -973,11 +1038,10 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
           q0 += real(0.5) * D * ja * ja; q1 += D * ja * jv; q2 += real(0.5) * D * jv * jv;
           if (j > 0) { real U = ja * m.fr[j - 1], V = jv * m.fr[j - 1]; UU += U * U; UV += U * V; VV += V * V; }
         }
-        k.q0 = q0; k.q1 = q1; k.q2 = q2;
-        k.U0 = k.jar[0] * m.mu; k.V0 = k.jv[0] * m.mu; k.UU = UU; k.UV = UV; k.VV = VV;
+        k.t.ls.q0 = q0; k.t.ls.q1 = q1; k.t.ls.q2 = q2;
+        k.t.ls.U0 = k.jar[0] * m.mu; k.t.ls.V0 = k.jv[0] * m.mu; k.t.ls.UU = UU; k.t.ls.UV = UV; k.t.ls.VV = VV;
       }
     }
-    wsync();
     real alpha = 0;
     int evals = 1;
     {
@@ -986,16 +1050,17 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       enum { W_P1 = 0, W_A, W_P1NEXT, W_MID, W_B1, W_B2, L_ACHECK, L_AFTERA, L_BCHECK, L_DOB2, L_ENDITER, L_FINAL, LS_DONE };
       const real gtol = m.tol * m.ls_tol * snorm * (m.meaninertia * NV);
       const int maxe = m.ls_iterations;
-      Pnt p0, p1, p2, pmid, p1next, p2next, c0, c1, c2;
+      Pnt p0, p1, p2, pmid, p1next, p2next, c0;
       p0.alpha = 0; p0.cost = cost; p0.d0 = gs; p0.d1 = -gs > 0 ? -gs : MINV;   // alpha = 0 is analytic (H search = -grad)
-      p1 = p2 = pmid = p1next = p2next = c0 = c1 = c2 = p0;
+      p1 = p2 = pmid = p1next = p2next = c0 = p0;
       int st = LS_DONE, dirn = 1;
       bool p2update = false, b1 = false, b2 = false;
       real aeval = 0;
       auto newton = [&](const Pnt& p) { return p.alpha - tdiv(p.d0, p.d1); };
-      auto bracket = [&](Pnt& p) {   // update_bracket against the candidates captured at the mid-point evaluation
+      // update_bracket against the candidates captured at the mid-point evaluation: (old p1next = c0, p2next, pmid)
+      auto bracket = [&](Pnt& p) {
         int flag = 0;
-        const Pnt* cand[3] = {&c0, &c1, &c2};
+        const Pnt* cand[3] = {&c0, &p2next, &pmid};
         for (int i = 0; i < 3; i++) {
           if (p.d0 < 0 && cand[i]->d0 < 0 && p.d0 < cand[i]->d0) { p = *cand[i]; flag = 1; }
           else if (p.d0 > 0 && cand[i]->d0 > 0 && p.d0 > cand[i]->d0) { p = *cand[i]; flag = 2; }
@@ -1009,8 +1074,10 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         if (!any(ev)) break;
         real c_ = 0, d0_ = 0, d1_ = 0;
         if (ev) {
-          TB_UNROLL1
-          for (int n = 0; n < ncon; n++) con_ls(con[n], m, aeval, c_, d0_, d1_);
+          if (nmine > 0) {
+            TB_UNROLL1
+            for (int s = 0; s < nmine; s++) con_ls(con_of(S, b, s), m, aeval, c_, d0_, d1_);
+          }
           c_ += aeval * aeval * qG2 + aeval * qG1 + gauss; d0_ += 2 * aeval * qG2 + qG1; d1_ += 2 * qG2;
         }
         Pnt r;
@@ -1032,8 +1099,8 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
             case W_P1NEXT: p1next = r; st = L_BCHECK; break;
             case W_MID: {
               pmid = r;
-              c0 = p1next; c1 = p2next; c2 = pmid;
-              const Pnt* cand[3] = {&c0, &c1, &c2};
+              c0 = p1next;
+              const Pnt* cand[3] = {&c0, &p2next, &pmid};
               int best = -1; real bestcost = 0;
               for (int i = 0; i < 3; i++)
                 if (tabs(cand[i]->d0) < gtol && (best == -1 || cand[i]->cost < bestcost)) { bestcost = cand[i]->cost; best = i; }
@@ -1079,17 +1146,23 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       if (alpha == 0) act = false;
       else {
         for (int k = 0; k < 6; k++) qacc[k] += alpha * search[k];
-        TB_UNROLL1
-        for (int n = 0; n < ncon; n++) for (int r = 0; r < 6; r++) con[n].jar[r] += alpha * con[n].jv[r];
+        if (nmine > 0) {
+          TB_UNROLL1
+          for (int s = 0; s < nmine; s++) {
+            Con<real>& c = con_of(S, b, s);
+            for (int r = 0; r < 6; r++) c.jar[r] += alpha * c.jv[r];
+          }
+        }
         iter++;
       }
     }
+    wsync();
   }
-  if (pass_on) {
-    if (nact_env > 0) {
-      for (int k = 0; k < 6; k++) B.warm[k] = qacc[k];
-      if (b == 0) { S.niter += iter; S.nls += nls; }
-    } else for (int k = 0; k < 6; k++) B.warm[k] = asm_[k];
+  if (pass_on) {   // the iterate back to body coordinates: it is the next warm start
+    real wl[3];
+    mulMTV(wl, R, qacc + 3);
+    for (int k = 0; k < 3; k++) qacc[3 + k] = wl[k];
+    if (nact_env > 0 && b == 0) { S.niter += iter; S.nls += nls; }
   }
   // ---------------- mj_checkAcc: a bad acceleration resets the env and repeats the forward pass
   if (!integ || pass == 1) break;
@@ -1097,7 +1170,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     bool bad = false;
     for (int k = 0; k < 6; k++) bad |= is_bad(qacc[k]);
     bad = grp_any(bad && on, base);
-    if (!any(bad)) break;
+    if (!uni_any(bad, aligned)) break;
     pass_on = on && bad;
     if (pass_on) { if (b == 0) S.bad |= 4; reset_data(); }
     wsync();
@@ -1109,7 +1182,12 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     // (M - h D) x = qfrc_smooth + qfrc_constraint on the bar's 6x6 block (Cholesky, packed lower)
     real A[21], x[6];
     for (int e = 0; e < 21; e++) A[e] = -h * Dblk[e];
-    for (int r = 0; r < 6; r++) { A[r * (r + 1) / 2 + r] += m.M[6 * b + r]; x[r] = fsm[r] + fcon[r]; }
+    {
+      real al[3], fl[3];
+      mulMTV(al, R, asm_ + 3); mulMTV(fl, R, fcon + 3);   // qacc_smooth and the constraint torque in body coordinates
+      for (int r = 0; r < 3; r++) { x[r] = Mb[r] * asm_[r] + fcon[r]; x[3 + r] = Mb[3 + r] * al[r] + fl[r]; }
+    }
+    for (int r = 0; r < 6; r++) A[r * (r + 1) / 2 + r] += Mb[r];
     TB_UNROLL
     for (int j = 0; j < 6; j++) {
       real s = A[j * (j + 1) / 2 + j];
@@ -1158,52 +1236,40 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
 }
 
 // mj_rnePostConstraint: cfrc_ext rows [torque; force] for world + 3 bars about the (stale) body positions, from the
-// contacts of the last pass; also the total bar-bar contact force magnitude (run.py:155-161).  Leaves S.u.cfrc.
+// contacts of the last pass; also the total bar-bar contact force magnitude (run.py:155-161).  Leaves S.cfrc.
 template <typename real>
-TB_FN void cfrc_stage(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, const Con<real>* con, int ncon) {
+TB_FN void cfrc_stage(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on) {
   const int b = L.bar, base = L.base;
-  // world row is taken about the mass-weighted centre of the three bars
-  real com[3] = {0, 0, 0}, mt = 0;
-  for (int bb = 0; bb < NBAR; bb++) { addscl3(com, S.xpos + 3 * bb, m.M[6 * bb]); mt += m.M[6 * bb]; }
-  scl3(com, com, 1 / mt);
   real own[6] = {0, 0, 0, 0, 0, 0}, world[6] = {0, 0, 0, 0, 0, 0}, barf = 0;
-  wsync();   // everyone has read xpos-independent union data; the union becomes cfrc
-  if (on) for (int k = 0; k < 24; k++) if (k / 6 == b + 1) S.u.cfrc[k] = 0;
-  wsync();
-  if (on) {
-    for (int n = 0; n < ncon; n++) {
-      const Con<real>& c = con[n];
-      real F[3], T[3], pos[3], r[3], tq[3];
-      con_wrench(c, F, T);
-      add3(pos, S.xpos + 3 * c.b2, c.r2);
-      if (c.b1 < 0) {
-        cross3(tq, c.r2, F);
-        for (int k = 0; k < 3; k++) { own[k] += tq[k] + T[k]; own[3 + k] += F[k]; }
-        sub3(r, pos, com); cross3(tq, r, F);
-        for (int k = 0; k < 3; k++) { world[k] -= tq[k] + T[k]; world[3 + k] -= F[k]; }
-      } else {
-        barf += tsqrt(c.force[0] * c.force[0] + c.force[1] * c.force[1] + c.force[2] * c.force[2]);
+  if (on && S.nact > 0) {
+    // the world row is taken about the mass-weighted centre of the three bars
+    real com[3] = {0, 0, 0}, mt = 0;
+    for (int bb = 0; bb < NBAR; bb++) { addscl3(com, S.xpos + 3 * bb, m.M[6 * bb]); mt += m.M[6 * bb]; }
+    scl3(com, com, 1 / mt);
+    for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
+      const Con<real>& c = con_of(S, o, s);
+      if (c.zone == ZONE_TOP) continue;
+      real t[3];
+      if (c.b2 == b) {
+        cross3(t, c.r2, c.wr);
+        for (int k = 0; k < 3; k++) { own[k] += t[k] + c.wr[3 + k]; own[3 + k] += c.wr[k]; }
+        if (c.b1 < 0) {
+          real pos[3], r[3];
+          add3(pos, S.xpos + 3 * b, c.r2); sub3(r, pos, com); cross3(t, r, c.wr);
+          for (int k = 0; k < 3; k++) { world[k] -= t[k] + c.wr[3 + k]; world[3 + k] -= c.wr[k]; }
+        }
+      } else if (c.b1 == b) {
+        cross3(t, c.r1, c.wr);
+        for (int k = 0; k < 3; k++) { own[k] -= t[k] + c.wr[3 + k]; own[3 + k] -= c.wr[k]; }
       }
+      if (c.b1 >= 0 && c.owner == b) barf += tsqrt(c.wr[0] * c.wr[0] + c.wr[1] * c.wr[1] + c.wr[2] * c.wr[2]);
     }
   }
   for (int k = 0; k < 6; k++) world[k] = sum3(world[k], base);
+  barf = sum3(barf, base);
   if (on) {
-    for (int k = 0; k < 6; k++) S.u.cfrc[6 * (b + 1) + k] = own[k];
-    if (b == 0) for (int k = 0; k < 6; k++) S.u.cfrc[k] = world[k];
-    if (b == 2) S.barforce = barf;
-  }
-  wsync();
-  if (on && b == 2) {   // bar-bar contacts: lane 2 adds them to the two bars' rows
-    for (int n = 0; n < ncon; n++) {
-      const Con<real>& c = con[n];
-      if (c.b1 < 0) continue;
-      real F[3], T[3], tq[3];
-      con_wrench(c, F, T);
-      cross3(tq, c.r2, F);
-      for (int k = 0; k < 3; k++) { S.u.cfrc[6 * (c.b2 + 1) + k] += tq[k] + T[k]; S.u.cfrc[6 * (c.b2 + 1) + 3 + k] += F[k]; }
-      cross3(tq, c.r1, F);
-      for (int k = 0; k < 3; k++) { S.u.cfrc[6 * (c.b1 + 1) + k] -= tq[k] + T[k]; S.u.cfrc[6 * (c.b1 + 1) + 3 + k] -= F[k]; }
-    }
+    for (int k = 0; k < 6; k++) S.cfrc[6 * (b + 1) + k] = own[k];
+    if (b == 0) { for (int k = 0; k < 6; k++) S.cfrc[k] = world[k]; S.barforce = barf; }
   }
   wsync();
 }

@@ -155,7 +155,7 @@ TB_NOINL void compute_obs(const EnvSh<real>& S, const EnvCfg& c, const Aux& A, d
       double Gm[9] = {-R[0], -R[1], R[2], -R[3], -R[4], R[5], -R[6], -R[7], R[8]};
       mat2quat_scipy(Gm, obs + 4 * b);
     }
-    for (int i = 0; i < 18; i++) obs[12 + i] = S.qvel[i];
+    for (int i = 0; i < 18; i++) obs[12 + i] = S.u.home.qvel[i];
     for (int i = 0; i < 9; i++) obs[30 + i] = (double)S.tlen[i];
     return;
   }
@@ -167,10 +167,10 @@ TB_NOINL void compute_obs(const EnvSh<real>& S, const EnvCfg& c, const Aux& A, d
   for (int i = 0; i < 18; i++) obs[i] = (double)S.sph[i] - cen[i % 3];
   if (nvel) for (int cap = 0; cap < 6; cap++) {
     int b = cap / 2;
-    double r[3], w[3] = {S.qvel[6 * b + 3], S.qvel[6 * b + 4], S.qvel[6 * b + 5]}, cr[3];
+    double r[3], w[3] = {S.u.home.qvel[6 * b + 3], S.u.home.qvel[6 * b + 4], S.u.home.qvel[6 * b + 5]}, cr[3];
     for (int k = 0; k < 3; k++) r[k] = (double)S.sph[3 * cap + k] - (double)S.xpos[3 * b + k];
     cross3(cr, w, r);  // local-frame angular velocity used as if world-frame (tr_env.py:599-604)
-    for (int k = 0; k < 3; k++) obs[18 + 3 * cap + k] = S.qvel[6 * b + k] + cr[k];
+    for (int k = 0; k < 3; k++) obs[18 + 3 * cap + k] = S.u.home.qvel[6 * b + k] + cr[k];
   }
   for (int i = 0; i < 9; i++) obs[18 + nvel + i] = (double)S.tlen[i];
   int base = 27 + nvel;
@@ -185,22 +185,24 @@ TB_NOINL void compute_obs(const EnvSh<real>& S, const EnvCfg& c, const Aux& A, d
 // do_simulation(ctrl, nsub) (integ) or mj_forward (integ = false, nsub = 1) on the env state in S, then
 // mj_rnePostConstraint.  Warp-collective.  The bar state is register-resident for the whole call.
 template <typename real>
-TB_NOINL void simulate(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, int nsub, bool integ) {
+TB_NOINL void simulate(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, int nsub, bool integ, bool aligned) {
   BarState<real> B;
   const int b = L.bar;
-  for (int k = 0; k < 3; k++) B.x[k] = (real)S.qpos[7 * b + k];
-  for (int k = 0; k < 4; k++) B.q[k] = (real)S.qpos[7 * b + 3 + k];
-  for (int k = 0; k < 6; k++) { B.v[k] = (real)S.qvel[6 * b + k]; B.warm[k] = (real)S.warm[6 * b + k]; }
-  Con<real> con[MAXCL];
-  int ncon = 0;
+  for (int k = 0; k < 3; k++) B.x[k] = (real)S.u.home.qpos[7 * b + k];
+  for (int k = 0; k < 4; k++) B.q[k] = (real)S.u.home.qpos[7 * b + 3 + k];
+  for (int k = 0; k < 6; k++) { B.v[k] = (real)S.u.home.qvel[6 * b + k]; B.warm[k] = (real)S.u.home.warm[6 * b + k]; }
   wsync();
   TB_UNROLL1
-  for (int s = 0; s < nsub; s++) phys(B, S, m, L, on, integ, con, ncon);
-  cfrc_stage(S, m, L, on, con, ncon);
+  for (int s = 0; s < nsub; s++) {
+    if (aligned) uni_any(true, true);   // the warps of the CTA enter every substep together
+    phys(B, S, m, L, on, integ, aligned);
+  }
+  cfrc_stage(S, m, L, on);
+  wsync();
   if (on) {
-    for (int k = 0; k < 3; k++) S.qpos[7 * b + k] = (double)B.x[k];
-    for (int k = 0; k < 4; k++) S.qpos[7 * b + 3 + k] = (double)B.q[k];
-    for (int k = 0; k < 6; k++) { S.qvel[6 * b + k] = (double)B.v[k]; S.warm[6 * b + k] = (double)B.warm[k]; }
+    for (int k = 0; k < 3; k++) S.u.home.qpos[7 * b + k] = (double)B.x[k];
+    for (int k = 0; k < 4; k++) S.u.home.qpos[7 * b + 3 + k] = (double)B.q[k];
+    for (int k = 0; k < 6; k++) { S.u.home.qvel[6 * b + k] = (double)B.v[k]; S.u.home.warm[6 * b + k] = (double)B.warm[k]; }
   }
   wsync();
 }
@@ -237,10 +239,10 @@ TB_NOINL void env_step_post(EnvSh<real>& S, const EnvCfg& c, Aux& A, StepOut& O)
   double healthy = c.terminate_when_unhealthy ? c.healthy_reward : 0.0;
   int delay = c.reward_delay_steps;
   bool finite = true;
-  for (int i = 0; i < NQ; i++) finite &= isfinite(S.qpos[i]);
-  for (int i = 0; i < NV; i++) finite &= isfinite(S.qvel[i]);
+  for (int i = 0; i < NQ; i++) finite &= isfinite(S.u.home.qpos[i]);
+  for (int i = 0; i < NV; i++) finite &= isfinite(S.u.home.qvel[i]);
   bool moving_any = false;
-  for (int i = 0; i < NV; i++) moving_any |= fabs(S.qvel[i]) > 0.1;
+  for (int i = 0; i < NV; i++) moving_any |= fabs(S.u.home.qvel[i]) > 0.1;
   bool healthy_turn = finite && moving_any;
   bool healthy_lin = finite && ((xvel > 1e-4 || xvel < -1e-4) || (yvel > 1e-4 || yvel < -1e-4));
   bool is_healthy = healthy_lin;
@@ -284,7 +286,7 @@ TB_NOINL void env_step_post(EnvSh<real>& S, const EnvCfg& c, Aux& A, StepOut& O)
   bool terminated = c.terminate_when_unhealthy ? !is_healthy : false;
   if (extra_term) terminated = true;
   double maxc = 0;
-  for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs((double)S.u.cfrc[i]));
+  for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs((double)S.cfrc[i]));
   if (maxc > c.kill_force) terminated = true;  // tr_env.py:480-481
   O.reward = fwd + healthy - ctrl_cost;
   O.fwd = fwd; O.ctrl_cost = ctrl_cost; O.healthy = healthy; O.psi = psi_info;
@@ -296,7 +298,7 @@ TB_NOINL void env_step_post(EnvSh<real>& S, const EnvCfg& c, Aux& A, StepOut& O)
 
 // one env.step(action) with the action in S.action -- warp-collective; obs NOT computed here
 template <typename real>
-TB_FN void env_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A, StepOut& O) {
+TB_FN void env_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A, StepOut& O, bool aligned) {
   const bool l0 = on && L.bar == 0;
   if (l0) {
     if (c.env_kind == ENV_TR) {  // _action_filter, k_FILTER = 1 (tr_env.py:680-683)
@@ -304,7 +306,7 @@ TB_FN void env_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
     } else for (int i = 0; i < NACT; i++) S.ctrl[i] = S.action[i];
   }
   wsync();
-  simulate(S, m, L, on, c.frame_skip, true);
+  simulate(S, m, L, on, c.frame_skip, true, aligned);
   if (l0) env_step_post(S, c, A, O);
   wsync();
 }
@@ -331,18 +333,18 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
   int idx = 0;
   if (l0) {
     // mj_resetData
-    for (int i = 0; i < NV; i++) { S.qvel[i] = 0; S.warm[i] = 0; }
+    for (int i = 0; i < NV; i++) { S.u.home.qvel[i] = 0; S.u.home.warm[i] = 0; }
     for (int i = 0; i < NACT; i++) { S.ctrl[i] = 0; S.act[i] = 0; }
     idx = (int)floor(u[0] * c.npose);
     if (idx > c.npose - 1) idx = c.npose - 1;
     if (idx < 0) idx = 0;
-    for (int i = 0; i < NQ; i++) S.qpos[i] = c.reset_pose[idx][i];
+    for (int i = 0; i < NQ; i++) S.u.home.qpos[i] = c.reset_pose[idx][i];
   }
   wsync();
   bool extra_set_state = (c.env_kind == ENV_TR) ? (c.task == TASK_TURN || c.task == TASK_TRACKING || c.task == TASK_AIMING)
                                                  : (c.task == TASK_TURN);
   int nfwd = (c.env_kind == ENV_TR ? 1 : 0) + (extra_set_state ? 1 : 0);
-  for (int k = 0; k < nfwd; k++) simulate(S, m, L, on, 1, false);  // set_state -> mj_forward
+  for (int k = 0; k < nfwd; k++) simulate(S, m, L, on, 1, false, false);  // set_state -> mj_forward
   if (l0) {
     // rotate the whole robot about world z by theta (positions and orientations), starting again from the table
     // pose: mj_kinematics normalised qpos in place, the reference re-uses its own copy
@@ -351,7 +353,7 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
     for (int b = 0; b < NBAR; b++) {
       double p[7];
       for (int k = 0; k < 7; k++) p[k] = c.reset_pose[idx][7 * b + k];
-      double* q = S.qpos + 7 * b;
+      double* q = S.u.home.qpos + 7 * b;
       q[0] = ct * p[0] - st * p[1]; q[1] = st * p[0] + ct * p[1]; q[2] = p[2];
       double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
       double w = p[3] / n, x = p[4] / n, y = p[5] / n, z = p[6] / n;
@@ -359,7 +361,7 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
     }
   }
   wsync();
-  simulate(S, m, L, on, 1, false);
+  simulate(S, m, L, on, 1, false, false);
   if (l0) {
     aux_from_forward(S, A);
     reset_setpoints(S, c);
@@ -371,10 +373,10 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
 template <typename real>
 TB_FN void reset_warm_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   if (c.env_kind == ENV_TR) {   // do_simulation, no filter
-    simulate(S, m, L, on, c.frame_skip, true);
+    simulate(S, m, L, on, c.frame_skip, true, false);
     if (on && L.bar == 0) aux_from_forward(S, A);
     wsync();
-  } else { StepOut O; env_step(S, m, c, L, on, A, O); }   // full self.step
+  } else { StepOut O; env_step(S, m, c, L, on, A, O, false); }   // full self.step
 }
 template <typename real>
 TB_FN void reset_finish(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
@@ -403,7 +405,7 @@ TB_FN void reset_finish(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, 
   wsync();
   if (c.env_kind == ENV_TR && (c.task == TASK_TURN || c.task == TASK_AIMING)) {
     StepOut O;
-    for (int k = 0; k < c.reward_delay_steps; k++) env_step(S, m, c, L, on, A, O);
+    for (int k = 0; k < c.reward_delay_steps; k++) env_step(S, m, c, L, on, A, O, false);
   }
   if (on && L.bar == 0) { A.ep_ret = 0; A.ep_len = 0; }
 }
@@ -413,9 +415,9 @@ template <typename real> TB_FN void load_env(EnvSh<real>& S, const LaneCtx& L, b
   if (on) {
     for (int i = L.bar; i < SO_XY_PREV; i += G) {
       double v = rec[i];
-      if (i < SO_QVEL) S.qpos[i] = v;
-      else if (i < SO_WARM) S.qvel[i - SO_QVEL] = v;
-      else if (i < SO_CTRL) S.warm[i - SO_WARM] = v;
+      if (i < SO_QVEL) S.u.home.qpos[i] = v;
+      else if (i < SO_WARM) S.u.home.qvel[i - SO_QVEL] = v;
+      else if (i < SO_CTRL) S.u.home.warm[i - SO_WARM] = v;
       else if (i < SO_ACT) S.ctrl[i - SO_CTRL] = v;
       else S.act[i - SO_ACT] = v;
     }
@@ -436,9 +438,9 @@ template <typename real> TB_FN void store_env(const EnvSh<real>& S, const LaneCt
   if (!on) return;
   for (int i = L.bar; i < SO_XY_PREV; i += G) {
     double v;
-    if (i < SO_QVEL) v = S.qpos[i];
-    else if (i < SO_WARM) v = S.qvel[i - SO_QVEL];
-    else if (i < SO_CTRL) v = S.warm[i - SO_WARM];
+    if (i < SO_QVEL) v = S.u.home.qpos[i];
+    else if (i < SO_WARM) v = S.u.home.qvel[i - SO_QVEL];
+    else if (i < SO_CTRL) v = S.u.home.warm[i - SO_WARM];
     else if (i < SO_ACT) v = S.ctrl[i - SO_CTRL];
     else v = S.act[i - SO_ACT];
     rec[i] = v;
@@ -476,7 +478,7 @@ constexpr int OBS_MAX = 160;
 
 // ---- the step of EPW consecutive envs starting at `first` (one warp)
 template <typename real>
-TB_FN void run_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first) {
+TB_FN void run_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first, bool aligned) {
   const int e = first + L.grp;
   const bool on = L.valid && e < io.n_envs, l0 = on && L.bar == 0;
   Aux A; StepOut O;
@@ -484,7 +486,7 @@ TB_FN void run_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
   load_env(S, L, on, A, rec, io.heading + (size_t)(on ? e : 0) * HEADING_SLOTS);
   if (l0) for (int i = 0; i < NACT; i++) S.action[i] = io.ctrl64 ? io.ctrl64[(size_t)e * NACT + i] : (double)io.ctrl32[(size_t)e * NACT + i];
   wsync();
-  env_step(S, m, c, L, on, A, O);
+  env_step(S, m, c, L, on, A, O, aligned);
   if (l0) {
     double obs[OBS_MAX];
     compute_obs(S, c, A, obs);
@@ -613,7 +615,7 @@ TB_FN void run_forward(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
   Aux A;
   double* rec = io.state + (size_t)(on ? e : 0) * STATE_STRIDE;
   load_env(S, L, on, A, rec, io.heading + (size_t)(on ? e : 0) * HEADING_SLOTS);
-  simulate(S, m, L, on, 1, false);
+  simulate(S, m, L, on, 1, false, false);
   if (l0) {
     aux_from_forward(S, A);
     double obs[OBS_MAX];

@@ -146,6 +146,7 @@ inline std::string make_model(const TsgModel& t, ModelT<real>& m, const float* h
   for (int k = 0; k < 2; k++) { m.ctrlrange[k] = (real)t.ctrlrange[k]; m.forcerange[k] = (real)t.forcerange[k]; }
   if (!(t.solref[0] < 0 && t.solref[1] < 0)) return "only direct (negative) solref is supported";
   if (t.condim != 6) return "condim must be 6";
+  if (t.friction[0] != t.friction[1] || t.friction[3] != t.friction[4]) return "friction must be isotropic (slide, slide, spin, roll, roll)";
   double dmax = fmin(MAXIMP_D, fmax(MINIMP_D, t.solimp[1]));
   m.K = (real)(-t.solref[0] / (dmax * dmax)); m.B = (real)(-t.solref[1] / dmax);
   for (int k = 0; k < 5; k++) { m.solimp[k] = (real)t.solimp[k]; m.fr[k] = (real)t.friction[k]; }

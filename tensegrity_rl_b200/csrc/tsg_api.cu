@@ -12,12 +12,17 @@
 using namespace tb;
 
 // Production configuration (profiles/): three lanes per env, ten envs per warp, TB_WARPS warps per CTA and
-// TB_MIN_CTAS CTAs per SM (the register cap follows: 65536 / (TB_MIN_CTAS * TB_WARPS * 32) per thread).
+// TB_MIN_CTAS CTAs per SM (the register cap follows: 65536 / (TB_MIN_CTAS * TB_WARPS * 32) per thread).  TB_ALIGN: the
+// warps of a CTA walk through an env step in phase (CTA barriers at every substep and Newton iteration), so that they
+// share fetched instructions.
 #ifndef TB_MIN_CTAS
-#define TB_MIN_CTAS 2
+#define TB_MIN_CTAS 1
 #endif
 #ifndef TB_WARPS
 #define TB_WARPS 5
+#endif
+#ifndef TB_ALIGN
+#define TB_ALIGN 1
 #endif
 
 static_assert(STATE_STRIDE == TSG_STATE_STRIDE && INFO_DIM == TSG_INFO_DIM && NDRAW == TSG_NDRAW, "ABI constants");
@@ -29,16 +34,21 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 template <typename real> __host__ __device__ constexpr size_t smem_model() { return align16(sizeof(ModelT<real>)); }
 constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
-template <typename real> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)TB_WARPS * EPW * align16(sizeof(EnvSh<real>)); }
+// env slices are spaced by an odd number of 16-byte units, so that the same field of the ten envs of a warp falls into different banks
+template <typename real> __host__ __device__ constexpr size_t envsh_stride() { return align16(sizeof(EnvSh<real>)) | 16; }
+template <typename real> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)TB_WARPS * EPW * envsh_stride<real>(); }
 
-// Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every warp pulls chunks of EPW
-// consecutive envs (then pool slots) from a global counter until the batch is done, so chunks of different cost
-// (contact count, Newton iterations, resets) balance dynamically.  The model constants are staged once per CTA in
-// shared memory.  Warps never synchronise with each other after that.
+// Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every CTA pulls rounds of TB_WARPS chunks
+// (a chunk = EPW consecutive envs, or pool slots, stepped by one warp) from a global counter until the batch is done,
+// so rounds of different cost (contact count, Newton iterations, resets) balance dynamically.  The env rounds come
+// first, then the pool rounds, so that all warps of a CTA always run the same program.  The model constants are
+// staged once per CTA in shared memory.
 template <typename real, int MODE>
 __global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<real>* __restrict__ gm,
-                                                                            const EnvCfg* __restrict__ gc, StepIO io) {
+                                                                            const EnvCfg* __restrict__ gc, StepIO io,
+                                                                            Con<real>* __restrict__ spill_base) {
   extern __shared__ __align__(16) unsigned char tb_smem[];
+  __shared__ int s_round;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(gm);
     uint32_t* dst = reinterpret_cast<uint32_t*>(tb_smem);
@@ -53,19 +63,24 @@ __global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(cons
   const LaneCtx L = make_lane();
   const int warp = threadIdx.x >> 5;
   EnvSh<real>& S = *reinterpret_cast<EnvSh<real>*>(tb_smem + smem_model<real>() + SMEM_CFG +
-                                                   (size_t)(warp * EPW + L.grp) * align16(sizeof(EnvSh<real>)));
-  const int env_chunks = (io.n_envs + EPW - 1) / EPW;
+                                                   (size_t)(warp * EPW + L.grp) * envsh_stride<real>());
+  if (L.valid && L.bar == 0) S.spill = spill_base + (size_t)((blockIdx.x * TB_WARPS + warp) * EPW + L.grp) * (3 * KS);
+  __syncwarp();
+  const int env_chunks = (io.n_envs + EPW - 1) / EPW, env_rounds = (env_chunks + TB_WARPS - 1) / TB_WARPS;
   const int pool_chunks = (MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? (io.n_pool + EPW - 1) / EPW : 0;
+  const int pool_rounds = (pool_chunks + TB_WARPS - 1) / TB_WARPS;
   for (;;) {
-    int chunk = 0;
-    if (L.lane == 0) chunk = atomicAdd(io.counter, 1);
-    chunk = shfl(chunk, 0);
-    if (chunk >= env_chunks + pool_chunks) break;
-    if (chunk < env_chunks) {
-      if (MODE == MODE_STEP) run_step(S, m, c, io, L, chunk * EPW);
-      else if (MODE == MODE_RESET) run_reset(S, m, c, io, L, chunk * EPW);
-      else run_forward(S, m, c, io, L, chunk * EPW);
-    } else run_pool(S, m, c, io, L, (chunk - env_chunks) * EPW, MODE == MODE_RESET);
+    __syncthreads();
+    if (threadIdx.x == 0) s_round = atomicAdd(io.counter, 1);
+    __syncthreads();
+    const int round = s_round;
+    if (round >= env_rounds + pool_rounds) break;
+    if (round < env_rounds) {
+      const int first = (round * TB_WARPS + warp) * EPW;   // may lie beyond the batch: the warp then idles in step
+      if (MODE == MODE_STEP) run_step(S, m, c, io, L, first, TB_ALIGN != 0);
+      else if (MODE == MODE_RESET) run_reset(S, m, c, io, L, first);
+      else run_forward(S, m, c, io, L, first);
+    } else run_pool(S, m, c, io, L, ((round - env_rounds) * TB_WARPS + warp) * EPW, MODE == MODE_RESET);
   }
 }
 
@@ -167,7 +182,7 @@ struct TsgHandle {
   // staging for the host-buffer entry points
   double *d_ctrl, *d_obs, *d_reward, *d_info, *d_termobs, *d_tmp;
   uint8_t* d_mask;
-  int* d_counter;
+  int* d_counter; void* d_spill;
   double* d_pool_obs; double* d_pool_real_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
   double* d_realobs_own;
@@ -201,7 +216,7 @@ template <typename real, int MODE>
 static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
   io.counter = h->d_counter + counter_slot;
   tb_env_kernel<real, MODE><<<h->grid[MODE], TB_WARPS * 32, smem_bytes<real>() + extra_smem(), s>>>(
-      (const ModelT<real>*)h->d_model, h->d_cfg, io);
+      (const ModelT<real>*)h->d_model, h->d_cfg, io, (Con<real>*)h->d_spill);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
@@ -223,8 +238,8 @@ static int setup_kernel(TsgHandle* h, int num_sms) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<real, MODE>, TB_WARPS * 32, smem));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
   // what is not carved out for shared memory stays L1, which serves the lanes' local memory (contacts, spills)
-  int chunks = (h->n_envs + EPW - 1) / EPW + (h->n_pool + EPW - 1) / EPW;
-  int need = (chunks + TB_WARPS - 1) / TB_WARPS, full = num_sms * per_sm;
+  int need = ((h->n_envs + EPW - 1) / EPW + TB_WARPS - 1) / TB_WARPS + ((h->n_pool + EPW - 1) / EPW + TB_WARPS - 1) / TB_WARPS;
+  int full = num_sms * per_sm;
   h->grid[MODE] = need < full ? need : full;
   if (MODE == MODE_STEP) {
     cudaFuncAttributes a;
@@ -241,6 +256,9 @@ static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
   CK(cudaMalloc(&h->d_model, sizeof(dm)));
   CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
   if (setup_kernel<real, MODE_STEP>(h, sms) || setup_kernel<real, MODE_RESET>(h, sms) || setup_kernel<real, MODE_FORWARD>(h, sms)) return -2;
+  int gmax = h->grid[0] > h->grid[1] ? h->grid[0] : h->grid[1];
+  if (h->grid[2] > gmax) gmax = h->grid[2];
+  CK(cudaMalloc(&h->d_spill, (size_t)gmax * TB_WARPS * EPW * (3 * KS) * sizeof(Con<real>)));   // contact slots beyond the shared-memory pool
   return 0;
 }
 
@@ -326,7 +344,7 @@ int tsg_destroy(TsgHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_cfg, h->d_hdata, h->d_qpos0, h->d_state, h->d_heading, h->d_draws, h->d_done, h->d_ctrl,
-                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_counter, h->d_pool_obs,
+                  h->d_obs, h->d_reward, h->d_info, h->d_termobs, h->d_tmp, h->d_mask, h->d_counter, h->d_spill, h->d_pool_obs,
                   h->d_pool_real_obs, h->d_lists, h->d_counts, h->d_need_sync, h->d_realobs_own};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -95,6 +95,7 @@ struct Emul {
   EnvCfg c;
   float* hdata;
   EnvSh<double> S[EPW];
+  Con<double> spill[EPW][3 * KS];
   int counter;
   unsigned long long seed; long long env_id; double* real_obs;
 };
@@ -114,6 +115,7 @@ const char* tbe_create(const TsgModel* model, const TsgEnvConfig* cfg, void** ou
   if (err.empty()) err = make_env_cfg(*cfg, *model, E->c);
   if (!err.empty()) { delete E; return err.c_str(); }
   memset(E->S, 0, sizeof(E->S));
+  for (int g = 0; g < EPW; g++) E->S[g].spill = E->spill[g];
   E->seed = 0; E->env_id = 0; E->real_obs = nullptr;
   *out = E;
   return nullptr;
@@ -147,7 +149,7 @@ void tbe_step(void* h, int n, double* rec, double* heading, const double* ctrl, 
   Emul* E = (Emul*)h;
   StepIO io = make_io(n, rec, heading, E);
   io.ctrl64 = ctrl; io.obs = obs; io.reward = reward; io.done = done; io.info = info;
-  run_warp([&]() { LaneCtx L = make_lane(); run_step(E->S[L.grp], E->m, E->c, io, L, 0); });
+  run_warp([&]() { LaneCtx L = make_lane(); run_step(E->S[L.grp], E->m, E->c, io, L, 0, false); });
 }
 void tbe_reset(void* h, int n, double* rec, double* heading, double* draws, int explicit_draws, unsigned long long seed,
                long long env_id, double* obs, const uint8_t* mask) {
@@ -186,11 +188,11 @@ void tbe_mj_step(void* h, int n, double* rec, const double* ctrl, int nstep, dou
     load_env(S, L, on, A, r, head);
     if (on && L.bar == 0) for (int i = 0; i < NACT; i++) S.ctrl[i] = ctrl[(size_t)L.grp * NACT + i];
     wsync();
-    simulate(S, E->m, L, on, nstep, true);
+    simulate(S, E->m, L, on, nstep, true, false);
     if (on && L.bar == 0) {
       int e = L.grp;
       if (ten_length) for (int i = 0; i < NTEN; i++) ten_length[e * NTEN + i] = S.tlen[i];
-      if (cfrc_ext) for (int i = 0; i < 24; i++) cfrc_ext[e * 24 + i] = S.u.cfrc[i];
+      if (cfrc_ext) for (int i = 0; i < 24; i++) cfrc_ext[e * 24 + i] = S.cfrc[i];
       if (stats) { int* s = stats + 6 * e; s[0] = S.nact; s[1] = S.niter; s[2] = S.nls; s[3] = S.nmpr; s[4] = S.overflow; s[5] = S.bad; }
     }
     wsync();

@@ -255,7 +255,7 @@ def test_pooled_reset_matches_reference_reset_semantics():
     from emul import emul as E
     L = E.lib()
     dr = np.zeros(10)
-    L.emul_make_draws(E.P(dr), C.c_ulonglong(9), C.c_ulonglong((1 << 40) + 0), C.c_ulonglong(0))
+    L.tbe_make_draws(E.P(dr), C.c_ulonglong(9), C.c_ulonglong((1 << 40) + 0), C.c_ulonglong(0))
     oe = OracleEnv("flat", "tr_env", desired_action="tracking")
     assert np.abs(oe.reset(dr) - o[0]).max() < 1e-6
     v.close()
