@@ -53,7 +53,11 @@ template <typename real>
 struct EnvSh {
   // world-frame exchange, rewritten by every pass; xpos / xmat / sph / tlen double as the "stale" kinematics the
   // reference's observation reads (positions lag qpos by one substep)
-  real xpos[9], xmat[27], vw[18], sph[18], tlen[NTEN], actdot[NACT];
+  real xpos[9], xmat[27], sph[18], tlen[NTEN];
+  union {
+    struct { real vw[18], actdot[NACT]; };   // world-frame velocities, activation derivatives (within a pass)
+    real cfrc[24];                           // mj_rnePostConstraint of the last pass
+  };
   double ctrl[NACT], act[NACT];
   union {
     struct { double qpos[NQ], qvel[NV], warm[NV]; } home;   // env state between physics calls (HBM record precision)
@@ -65,15 +69,15 @@ struct EnvSh {
       real xv[NV];        // world-frame twists of the vector under J; during the solve: the block rows' partial solutions
     } sol;
   } u;
-  real cfrc[24];          // mj_rnePostConstraint of the last pass
+#if TB_KP > 0
   Con<real> con[NCS];
+#endif
   Con<real>* spill;       // global memory: 3 * KS slots of this env-in-flight
   int ncl[3];             // contacts owned by each lane
   int cpl[3];             // which blocks below the diagonal exist (set by the pair owners)
   int nact, overflow, bad, niter, nls, nmpr;
   real barforce;
-  // env layer (lane 0 of the env)
-  double action[NACT], draws[NDRAW + 2];
+  double action[NACT];    // env layer (lane 0 of the env)
 };
 
 struct LaneCtx { int lane, grp, bar, base; bool valid; };
@@ -105,7 +109,12 @@ TB_FN bool uni_any(bool p, bool aligned) {
 template <typename real> struct BarState { real x[3], q[4], v[6], warm[6]; };
 
 // k-th contact of lane `owner`
-template <typename real> TB_FN Con<real>& con_of(EnvSh<real>& S, int owner, int k) { return k < KP ? S.con[owner * KP + k] : S.spill[owner * KS + k - KP]; }
+template <typename real> TB_FN Con<real>& con_of(EnvSh<real>& S, int owner, int k) {
+#if TB_KP > 0
+  if (k < KP) return S.con[owner * KP + k];
+#endif
+  return S.spill[owner * KS + k - KP];
+}
 
 // ------------------------------------------------------------------ contact helpers
 template <typename real> TB_FN void make_frame(real* f) {
@@ -666,39 +675,42 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   publish(asm_, pass_on);
   // ---------------- collision
   int nmine = 0, nmpr = 0;
-  if (pass_on) {
-    if (m.floor_type == 0) {
-      TB_UNROLL1
-      for (int g = 0; g < 5; g++) {
-        const int Gi = 5 * b + g;
-        real c[3], tmp[3];
-        mulMV(c, R, m.gpos[Gi]); add3(c, c, B.x);
-        sub3(tmp, c, m.fpos);
-        real cdist = dot3(tmp, m.fnormal);
-        if (m.gtype[Gi] == GEOM_SPHERE) {
-          real r = m.gsize[Gi][0];
-          if (cdist <= r) {
-            real dist = cdist - r, pos[3];
-            copy3(pos, c); addscl3(pos, m.fnormal, -dist / 2 - r);
-            add_contact(S, b, nmine, -1, b, dist, pos, m.fnormal);
-          }
-        } else if (cdist <= m.gbound[Gi]) {
-          real axis[3] = {R[2], R[5], R[8]}, xaxis[3] = {R[0], R[3], R[6]}, dist[4], pts[4][3];
-          int cnt = 0;
-          plane_cylinder_points(m, c, axis, m.gsize[Gi][0], m.gsize[Gi][1], xaxis, cnt, dist, pts);
-          for (int k = 0; k < cnt; k++) add_contact(S, b, nmine, -1, b, dist[k], pts[k], m.fnormal);
+  if (pass_on && m.floor_type == 0) {
+    TB_UNROLL1
+    for (int g = 0; g < 5; g++) {
+      const int Gi = 5 * b + g;
+      real c[3], tmp[3];
+      for (int k = 0; k < 3; k++) c[k] = B.x[k] + R[3 * k + 2] * m.gz[Gi];
+      sub3(tmp, c, m.fpos);
+      real cdist = dot3(tmp, m.fnormal);
+      if (m.gtype[Gi] == GEOM_SPHERE) {
+        real r = m.gsize[Gi][0];
+        if (cdist <= r) {
+          real dist = cdist - r, pos[3];
+          copy3(pos, c); addscl3(pos, m.fnormal, -dist / 2 - r);
+          add_contact(S, b, nmine, -1, b, dist, pos, m.fnormal);
         }
+      } else if (cdist <= m.gbound[Gi]) {
+        real axis[3] = {R[2], R[5], R[8]}, xaxis[3] = {R[0], R[3], R[6]}, dist[4], pts[4][3];
+        int cnt = 0;
+        plane_cylinder_points(m, c, axis, m.gsize[Gi][0], m.gsize[Gi][1], xaxis, cnt, dist, pts);
+        for (int k = 0; k < cnt; k++) add_contact(S, b, nmine, -1, b, dist[k], pts[k], m.fnormal);
       }
-    } else {
-      // height field (frame axis-aligned at fpos): per geom, the prisms under its AABB whose top reaches the AABB's
-      // bottom (MuJoCo's test) and that the geom can reach (conservative cull), each through MPR
-      TB_UNROLL1
-      for (int g = 0; g < 5; g++) {
-        const int Gi = 5 * b + g;
-        real gc[3], pos[3];
-        mulMV(gc, R, m.gpos[Gi]); add3(gc, gc, B.x);
-        sub3(pos, gc, m.fpos);
-        const real r = m.gsize[Gi][0], hl = m.gsize[Gi][1], rb = m.gbound[Gi];
+    }
+  }
+  if (m.floor_type != 0) {
+    // height field (frame axis-aligned at fpos): per geom, the prisms under its AABB whose top reaches the AABB's
+    // bottom (MuJoCo's test) and that the geom can reach (conservative cull) are listed in a bit mask; the lanes of
+    // the warp then take their candidates through MPR round by round, together
+    TB_UNROLL1
+    for (int g = 0; g < 5; g++) {
+      const int Gi = 5 * b + g;
+      unsigned cand = 0;
+      int cmin = 0, rmin = 0, per_row = 1;
+      real gc[3], pos[3];
+      for (int k = 0; k < 3; k++) { gc[k] = B.x[k] + R[3 * k + 2] * m.gz[Gi]; pos[k] = gc[k] - m.fpos[k]; }
+      const real r = m.gsize[Gi][0], hl = m.gsize[Gi][1], rb = m.gbound[Gi];
+      if (pass_on) {
         bool ok = true;
         for (int i = 0; i < 2; i++) if (m.hsize[i] < pos[i] - rb || -m.hsize[i] > pos[i] + rb) ok = false;
         if (m.hsize[2] < pos[2] - rb || -m.hsize[3] > pos[2] + rb) ok = false;
@@ -711,101 +723,137 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         real xmin = pos[0] - ext[0], xmax = pos[0] + ext[0], ymin = pos[1] - ext[1], ymax = pos[1] + ext[1];
         real zmin = pos[2] - ext[2], zmax = pos[2] + ext[2];
         if (xmin > m.hsize[0] || xmax < -m.hsize[0] || ymin > m.hsize[1] || ymax < -m.hsize[1] || zmin > m.hsize[2] || zmax < -m.hsize[3]) ok = false;
-        if (!ok) continue;
-        int cmin = (int)tfloor((xmin + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
-        int cmax = (int)tceil((xmax + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
-        int rmin = (int)tfloor((ymin + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
-        int rmax = (int)tceil((ymax + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
-        if (cmin < 0) cmin = 0;
-        if (cmax > m.ncol - 1) cmax = m.ncol - 1;
-        if (rmin < 0) rmin = 0;
-        if (rmax > m.nrow - 1) rmax = m.nrow - 1;
-        const int per_row = 2 * (cmax - cmin + 1) - 2;
-        if (per_row <= 0 || rmax <= rmin) continue;
-        CObj<real> o2;
-        o2.type = m.gtype[Gi]; copy3(o2.pos, pos); o2.size[0] = r; o2.size[1] = hl;
-        for (int k = 0; k < 9; k++) o2.R[k] = R[k];
-        TB_UNROLL1
-        for (int rr = rmin; rr < rmax; rr++) {
-          TB_UNROLL1
-          for (int k = 0; k < per_row; k++) {
-            CObj<real> o1;
-            o1.type = 100;
-            hf_prism(m, rr, cmin, k, o1);
-            if (!(o1.pz[0] >= zmin || o1.pz[1] >= zmin || o1.pz[2] >= zmin)) continue;
-            if (hf_above_top_plane(o1, o2.type, pos, R, r, hl)) continue;
-            real depth = 0, dir[3] = {0, 0, 1}, cp[3] = {0, 0, 0};
-            nmpr++;
-            bool hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, dir, cp);
-            if (hit && ccd_vec_is_origin(dir)) hit = false;
-            if (hit) {
-              add3(cp, cp, m.fpos);
-              if ((m.flags & 4u) && o2.type == GEOM_SPHERE) {
-                real nn[3]; sub3(nn, gc, cp);
-                if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(dir, nn); }
-              }
-              add_contact(S, b, nmine, -1, b, -depth, cp, dir);
+        if (ok) {
+          cmin = (int)tfloor((xmin + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
+          int cmax = (int)tceil((xmax + m.hsize[0]) / (2 * m.hsize[0]) * (m.ncol - 1));
+          rmin = (int)tfloor((ymin + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
+          int rmax = (int)tceil((ymax + m.hsize[1]) / (2 * m.hsize[1]) * (m.nrow - 1));
+          if (cmin < 0) cmin = 0;
+          if (cmax > m.ncol - 1) cmax = m.ncol - 1;
+          if (rmin < 0) rmin = 0;
+          if (rmax > m.nrow - 1) rmax = m.nrow - 1;
+          per_row = 2 * (cmax - cmin + 1) - 2;
+          if (per_row > 0 && rmax > rmin) {
+            if (per_row * (rmax - rmin) > 32) S.overflow = 1;
+            TB_UNROLL1
+            for (int q = 0; q < per_row * (rmax - rmin) && q < 32; q++) {
+              CObj<real> o1;
+              hf_prism(m, rmin + q / per_row, cmin, q % per_row, o1);
+              if (!(o1.pz[0] >= zmin || o1.pz[1] >= zmin || o1.pz[2] >= zmin)) continue;
+              if (hf_above_top_plane(o1, m.gtype[Gi], pos, R, r, hl)) continue;
+              cand |= 1u << q;
             }
+          } else per_row = 1;
+        }
+      }
+      TB_UNROLL1
+      while (any(cand != 0)) {
+        const bool has = cand != 0;
+        CObj<real> o1, o2;
+        o1 = CObj<real>(); o2 = o1;
+        if (has) {
+          const int q = lowbit(cand);
+          cand &= cand - 1;
+          o1.type = 100;
+          hf_prism(m, rmin + q / per_row, cmin, q % per_row, o1);
+          o2.type = m.gtype[Gi]; copy3(o2.pos, pos); o2.size[0] = r; o2.size[1] = hl;
+          for (int k = 0; k < 9; k++) o2.R[k] = R[k];
+          nmpr++;
+        }
+        real depth = 0, dir[3] = {0, 0, 1}, cp[3] = {0, 0, 0};
+        bool hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, has, &depth, dir, cp);
+        if (has) {
+          if (hit && ccd_vec_is_origin(dir)) hit = false;
+          if (hit) {
+            add3(cp, cp, m.fpos);
+            if ((m.flags & 4u) && o2.type == GEOM_SPHERE) {
+              real nn[3]; sub3(nn, gc, cp);
+              if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(dir, nn); }
+            }
+            add_contact(S, b, nmine, -1, b, -depth, cp, dir);
           }
         }
       }
     }
-    // bar-bar: this lane takes pair p = its bar index: (0,1), (0,2), (1,2).  25 geom pairs: bounding spheres, analytic
-    // capsule bound (conservative: MPR reports penetration only for intersecting shapes), then sphere-sphere / MPR
-    {
-      const int p = b, pb1 = p == 2 ? 1 : 0, pb2 = p == 0 ? 1 : 2;
-      const real *X1 = S.xpos + 3 * pb1, *X2 = S.xpos + 3 * pb2, *R1 = S.xmat + 9 * pb1, *R2 = S.xmat + 9 * pb2;
+  }
+  // bar-bar: this lane takes pair p = its bar index: (0,1), (0,2), (1,2).  All geoms lie on their bar's axis, so the 25
+  // geom pairs are filtered with scalars: MuJoCo's bounding-sphere test, then an analytic capsule bound (conservative:
+  // MPR reports penetration only for intersecting shapes).  Sphere-sphere pairs are analytic; the others are listed in
+  // a bit mask and the lanes of the warp take their candidates through MPR round by round, together.
+  {
+    const int pb1 = b == 2 ? 1 : 0, pb2 = b == 0 ? 1 : 2;
+    const real *X1 = S.xpos + 3 * pb1, *X2 = S.xpos + 3 * pb2, *R1 = S.xmat + 9 * pb1, *R2 = S.xmat + 9 * pb2;
+    unsigned cand = 0;
+    if (pass_on) {
+      const real a1[3] = {R1[2], R1[5], R1[8]}, a2[3] = {R2[2], R2[5], R2[8]};
+      real D[3]; sub3(D, X1, X2);
+      const real DD = dot3(D, D), Da1 = dot3(D, a1), Da2 = dot3(D, a2), a12 = dot3(a1, a2);
       TB_UNROLL1
       for (int i = 0; i < 25; i++) {
-        int g1 = 5 * pb1 + i / 5, g2 = 5 * pb2 + i % 5;
-        int cb1 = pb1, cb2 = pb2;
-        const real *Ra = R1, *Rb = R2;
-        real c1[3], c2[3];
-        mulMV(c1, R1, m.gpos[g1]); add3(c1, c1, X1);
-        mulMV(c2, R2, m.gpos[g2]); add3(c2, c2, X2);
-        real dd[3]; sub3(dd, c1, c2);
-        real bs = m.gbound[g1] + m.gbound[g2];
-        real d2c = dot3(dd, dd);
-        if (d2c > bs * bs) continue;   // MuJoCo's own bounding-sphere test
-        int t1 = m.gtype[g1], t2 = m.gtype[g2];
-        real rs = m.gsize[g1][0] + m.gsize[g2][0] + real(1e-6);
-        real a1[3] = {R1[2] * m.gsize[g1][1], R1[5] * m.gsize[g1][1], R1[8] * m.gsize[g1][1]};
-        real a2[3] = {R2[2] * m.gsize[g2][1], R2[5] * m.gsize[g2][1], R2[8] * m.gsize[g2][1]};
+        const int g1 = 5 * pb1 + i / 5, g2 = 5 * pb2 + i % 5;
+        const real z1 = m.gz[g1], z2 = m.gz[g2];
+        // centre difference r = D + z1 a1 - z2 a2
+        const real rr = DD + z1 * z1 + z2 * z2 + 2 * (z1 * Da1 - z2 * Da2 - z1 * z2 * a12);
+        const real bs = m.gbound[g1] + m.gbound[g2];
+        if (rr > bs * bs) continue;   // MuJoCo's own bounding-sphere test
+        const int t1 = m.gtype[g1], t2 = m.gtype[g2];
+        const real rs = m.gsize[g1][0] + m.gsize[g2][0] + real(1e-6), h1 = m.gsize[g1][1], h2 = m.gsize[g2][1];
+        const real ra1 = Da1 + z1 - z2 * a12, ra2 = Da2 + z1 * a12 - z2;   // a1 . r, a2 . r
         real d2;
-        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) d2 = d2c;
-        else if (t1 == GEOM_SPHERE) d2 = ptseg_dist2(c1, c2, a2);
-        else if (t2 == GEOM_SPHERE) d2 = ptseg_dist2(c2, c1, a1);
-        else d2 = segseg_dist2(c1, a1, c2, a2);
+        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) d2 = rr;
+        else if (t1 == GEOM_SPHERE) { real t = clampr(tdiv(ra2, h2), real(-1), real(1)); d2 = rr - 2 * t * h2 * ra2 + t * t * h2 * h2; }
+        else if (t2 == GEOM_SPHERE) { real t = clampr(tdiv(-ra1, h1), real(-1), real(1)); d2 = rr + 2 * t * h1 * ra1 + t * t * h1 * h1; }
+        else {
+          const real A = h1 * h1, E = h2 * h2, Bq = h1 * h2 * a12, C = h1 * ra1, F = h2 * ra2;
+          real den = A * E - Bq * Bq, sg = 0, t;
+          if (den > real(1e-30)) sg = clampr(tdiv(Bq * F - C * E, den), real(-1), real(1));
+          t = tdiv(Bq * sg + F, E);
+          if (t < real(-1)) { t = real(-1); sg = clampr(tdiv(-Bq - C, A), real(-1), real(1)); }
+          else if (t > real(1)) { t = real(1); sg = clampr(tdiv(Bq - C, A), real(-1), real(1)); }
+          d2 = rr + sg * sg * A + t * t * E + 2 * (sg * C - t * F - sg * t * Bq);
+        }
         if (!(d2 <= rs * rs)) continue;
-        if (t1 > t2) {   // lower geom type first
-          int ti = g1; g1 = g2; g2 = ti; ti = cb1; cb1 = cb2; cb2 = ti;
-          for (int k = 0; k < 3; k++) { real tv = c1[k]; c1[k] = c2[k]; c2[k] = tv; }
-          const real* tp = Ra; Ra = Rb; Rb = tp;
-        }
-        bool hit;
-        real dist = 1, pos[3] = {0, 0, 0}, nrm[3] = {1, 0, 0};
-        nmpr++;
-        if (m.gtype[g2] == GEOM_SPHERE) {
+        if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) {
+          real c1[3], c2[3], nrm[3], pos[3];
+          for (int k = 0; k < 3; k++) { c1[k] = X1[k] + a1[k] * z1; c2[k] = X2[k] + a2[k] * z2; }
           sub3(nrm, c2, c1);
-          real len = normalize3(nrm), r1 = m.gsize[g1][0];
-          dist = len - r1 - m.gsize[g2][0];
-          hit = dist <= 0;
+          real len = normalize3(nrm), r1 = m.gsize[g1][0], dist = len - r1 - m.gsize[g2][0];
+          nmpr++;
           copy3(pos, c1); addscl3(pos, nrm, r1 + dist / 2);
-        } else {
-          CObj<real> o1, o2;
-          o1.type = m.gtype[g1]; copy3(o1.pos, c1); o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
-          o2.type = m.gtype[g2]; copy3(o2.pos, c2); o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
-          for (int k = 0; k < 9; k++) { o1.R[k] = Ra[k]; o2.R[k] = Rb[k]; }
-          real depth;
-          hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, &depth, nrm, pos);
-          if (hit && ccd_vec_is_origin(nrm)) hit = false;
-          dist = -depth;
-          if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
-            real nn[3]; sub3(nn, pos, c1);
-            if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(nrm, nn); }
-          }
+          if (dist <= 0) add_contact(S, b, nmine, pb1, pb2, dist, pos, nrm);
+        } else cand |= 1u << i;
+      }
+    }
+    TB_UNROLL1
+    while (any(cand != 0)) {
+      const bool has = cand != 0;
+      int cb1 = pb1, cb2 = pb2;
+      CObj<real> o1, o2;
+      o1 = CObj<real>(); o2 = o1;
+      if (has) {
+        const int i = lowbit(cand);
+        cand &= cand - 1;
+        int g1 = 5 * pb1 + i / 5, g2 = 5 * pb2 + i % 5;
+        const real *Ra = R1, *Rb = R2, *Xa = X1, *Xb = X2;
+        if (m.gtype[g1] > m.gtype[g2]) {   // lower geom type first
+          int ti = g1; g1 = g2; g2 = ti; cb1 = pb2; cb2 = pb1;
+          Ra = R2; Rb = R1; Xa = X2; Xb = X1;
         }
-        if (hit) add_contact(S, b, nmine, cb1, cb2, dist, pos, nrm);
+        o1.type = m.gtype[g1]; o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
+        o2.type = m.gtype[g2]; o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
+        for (int k = 0; k < 9; k++) { o1.R[k] = Ra[k]; o2.R[k] = Rb[k]; }
+        for (int k = 0; k < 3; k++) { o1.pos[k] = Xa[k] + Ra[3 * k + 2] * m.gz[g1]; o2.pos[k] = Xb[k] + Rb[3 * k + 2] * m.gz[g2]; }
+        nmpr++;
+      }
+      real depth = 0, nrm[3] = {1, 0, 0}, pos[3] = {0, 0, 0};
+      bool hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, has, &depth, nrm, pos);
+      if (has) {
+        if (hit && ccd_vec_is_origin(nrm)) hit = false;
+        if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
+          real nn[3]; sub3(nn, pos, o1.pos);
+          if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(nrm, nn); }
+        }
+        if (hit) add_contact(S, b, nmine, cb1, cb2, -depth, pos, nrm);
       }
     }
   }

@@ -15,6 +15,7 @@ struct Aux {  // env bookkeeping (valid in lane 0 of the env)
   double step_num, ep_ret, ep_len, xvel, yvel;
   int head_n, head_pos;
   double* heading;  // [HEADING_SLOTS] in global memory
+  const double* draws;  // [NDRAW] in global memory: the random draws of the env's current reset
 };
 struct StepOut {
   double reward, fwd, ctrl_cost, healthy, psi, xy[2];
@@ -317,9 +318,9 @@ template <typename real> TB_FN void aux_from_forward(const EnvSh<real>& S, Aux& 
 }
 
 // env.reset() = MujocoEnv.reset (mj_resetData) + reset_model, in three pieces so that it can run either in one go
-// (tsg_reset) or one warm-up step per launch on a background pool slot.  Random draws in S.draws.
-template <typename real> TB_FN void reset_setpoints(EnvSh<real>& S, const EnvCfg& c) {  // lane 0
-  const double* u = S.draws;
+// (tsg_reset) or one warm-up step per launch on a background pool slot.  Random draws: A.draws.
+template <typename real> TB_FN void reset_setpoints(EnvSh<real>& S, const EnvCfg& c, const Aux& A) {  // lane 0
+  const double* u = A.draws;
   for (int i = 0; i < NACT; i++) {
     double t = u[2 + i] * c.tendon_reset_stdev + c.tendon_reset_mean;
     if (t > c.tendon_max_length) t = c.tendon_max_length; else if (t < c.tendon_min_length) t = c.tendon_min_length;
@@ -329,7 +330,7 @@ template <typename real> TB_FN void reset_setpoints(EnvSh<real>& S, const EnvCfg
 template <typename real>
 TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   const bool l0 = on && L.bar == 0;
-  const double* u = S.draws;
+  const double* u = A.draws;
   int idx = 0;
   if (l0) {
     // mj_resetData
@@ -364,7 +365,7 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
   simulate(S, m, L, on, 1, false, false);
   if (l0) {
     aux_from_forward(S, A);
-    reset_setpoints(S, c);
+    reset_setpoints(S, c, A);
     if (c.env_kind == ENV_TR) for (int i = 0; i < NACT; i++) S.ctrl[i] = S.action[i];
   }
   wsync();
@@ -381,7 +382,7 @@ TB_FN void reset_warm_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& 
 template <typename real>
 TB_FN void reset_finish(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   if (on && L.bar == 0) {
-    const double* u = S.draws;
+    const double* u = A.draws;
     Pose P; read_pose(S, P);
     A.reset_psi = P.psi;
     double lo = c.waypt_range[0], hi = c.waypt_range[1];
@@ -529,11 +530,9 @@ TB_FN void run_reset(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, con
   if (l0) {
     if (io.term_obs && io.obs) for (int i = 0; i < c.obs_dim; i++) io.term_obs[(size_t)e * c.obs_dim + i] = io.obs[(size_t)e * c.obs_dim + i];
     nreset = rec[SO_NRESET];
-    if (io.explicit_draws) for (int i = 0; i < NDRAW; i++) S.draws[i] = io.draws[(size_t)e * NDRAW + i];
-    else {
-      make_draws(S.draws, io.seed, (unsigned long long)(io.env_id_base + e), (unsigned long long)nreset);
-      if (io.draws) for (int i = 0; i < NDRAW; i++) io.draws[(size_t)e * NDRAW + i] = S.draws[i];
-    }
+    double* dr = io.draws + (size_t)e * NDRAW;
+    if (!io.explicit_draws) make_draws(dr, io.seed, (unsigned long long)(io.env_id_base + e), (unsigned long long)nreset);
+    A.draws = dr;
   }
   wsync();
   reset_begin(S, m, c, L, on, A);
@@ -571,15 +570,14 @@ TB_FN void run_pool(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
   double nreset = 0;
   if (l0) {
     nreset = rec[SO_NRESET];
-    if (phase == 0) {
-      make_draws(S.draws, io.seed, (1ull << 40) + (unsigned long long)(io.env_id_base + p), (unsigned long long)nreset);
-      for (int i = 0; i < NDRAW; i++) io.draws[row * NDRAW + i] = S.draws[i];
-    } else for (int i = 0; i < NDRAW; i++) S.draws[i] = io.draws[row * NDRAW + i];
+    double* dr = io.draws + row * NDRAW;
+    if (phase == 0) make_draws(dr, io.seed, (1ull << 40) + (unsigned long long)(io.env_id_base + p), (unsigned long long)nreset);
+    A.draws = dr;
   }
   wsync();
   const bool begin = on && phase == 0;
   if (any(begin)) reset_begin(S, m, c, L, begin, A);
-  if (l0 && phase != 0) reset_setpoints(S, c);
+  if (l0 && phase != 0) reset_setpoints(S, c, A);
   wsync();
   bool warming = on;
   do {

@@ -51,6 +51,7 @@ struct ModelT {
   real gsize[NGEOM][2];
   real gpos[NGEOM][3];
   real gbound[NGEOM];   // bounding-sphere radius of the geom about its centre
+  real gz[NGEOM];       // position of the geom's centre along the bar axis (all geoms lie on it)
   // tendons
   int tbody[NEND];
   real tsite[NEND][3];
@@ -113,6 +114,8 @@ inline std::string make_model(const TsgModel& t, ModelT<real>& m, const float* h
       m.gsize[G][0] = (real)r; m.gsize[G][1] = (real)hl;
       m.gbound[G] = (real)(m.gtype[G] == GEOM_SPHERE ? r : sqrt(r * r + hl * hl));
       for (int k = 0; k < 3; k++) m.gpos[G][k] = (real)t.geom_pos[b][g][k];
+      if (t.geom_pos[b][g][0] != 0 || t.geom_pos[b][g][1] != 0) return "geoms must be centred on the bar axis";
+      m.gz[G] = (real)t.geom_pos[b][g][2];
       // geom frames must be the body frame up to axis flips (cylinders/spheres are symmetric under those)
       const double* q = t.geom_quat[b][g];
       int big = 0;

@@ -55,28 +55,30 @@ template <typename real> TB_FN void obj_center(const CObj<real>& o, real* c) {
     c[0] /= 6; c[1] /= 6; c[2] /= 6;
   } else copy3(c, o.pos);
 }
-template <typename real> TB_NOINL void mink_support(const CObj<real>& o1, const CObj<real>& o2, const real* dir, Supp<real>& s) {
+template <typename real> TB_FN void mink_support(const CObj<real>& o1, const CObj<real>& o2, const real* dir, Supp<real>& s) {
   real nd[3] = {-dir[0], -dir[1], -dir[2]}, v2[3];
   obj_support(o1, dir, s.v1);
   obj_support(o2, nd, v2);
   sub3(s.v, s.v1, v2);
 }
-template <typename real> TB_FN void portal_dir(const Supp<real>* p, real* dir) {
+template <typename real> TB_FN void portal_dir(const Supp<real>& p1, const Supp<real>& p2, const Supp<real>& p3, real* dir) {
   real a[3], b[3];
-  sub3(a, p[2].v, p[1].v); sub3(b, p[3].v, p[1].v);
+  sub3(a, p2.v, p1.v); sub3(b, p3.v, p1.v);
   cross3(dir, a, b); ccd_normalize(dir);
 }
-template <typename real> TB_FN bool portal_reach_tol(const Supp<real>* p, const Supp<real>& v4, const real* dir, real tol) {
+template <typename real>
+TB_FN bool portal_reach_tol(const Supp<real>& p1, const Supp<real>& p2, const Supp<real>& p3, const Supp<real>& v4, const real* dir, real tol) {
   real dv4 = dot3(v4.v, dir);
-  real d1 = dv4 - dot3(p[1].v, dir), d2 = dv4 - dot3(p[2].v, dir), d3 = dv4 - dot3(p[3].v, dir);
+  real d1 = dv4 - dot3(p1.v, dir), d2 = dv4 - dot3(p2.v, dir), d3 = dv4 - dot3(p3.v, dir);
   d1 = tmin(d1, d2); d1 = tmin(d1, d3);
   return ccd_eq(d1, tol) || d1 < tol;
 }
-template <typename real> TB_FN void expand_portal(Supp<real>* p, const Supp<real>& v4) {
+template <typename real>
+TB_FN void expand_portal(const Supp<real>& p0, Supp<real>& p1, Supp<real>& p2, Supp<real>& p3, const Supp<real>& v4) {
   real v4v0[3];
-  cross3(v4v0, v4.v, p[0].v);
-  if (dot3(p[1].v, v4v0) > 0) { if (dot3(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4; }
-  else { if (dot3(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4; }
+  cross3(v4v0, v4.v, p0.v);
+  if (dot3(p1.v, v4v0) > 0) { if (dot3(p2.v, v4v0) > 0) p1 = v4; else p3 = v4; }
+  else { if (dot3(p3.v, v4v0) > 0) p2 = v4; else p1 = v4; }
 }
 template <typename real> TB_FN real seg_dist2_origin(const real* x0, const real* b, real* wit) {
   real d[3];
@@ -109,100 +111,134 @@ template <typename real> TB_FN real tri_dist2_origin(const real* x0, const real*
   }
   return dist;
 }
-// returns true on penetration; dir points from obj1 to obj2
+
+// MPR for the lanes of a warp that have a pair (`has`), in lock step: the algorithm is run as a per-lane state
+// machine in which every tick is ONE Minkowski support query plus the bookkeeping of the phase the lane is in
+// (portal discovery / refinement / penetration search), so lanes whose searches take different paths still share the
+// instruction stream, and the portal lives in registers.  Warp-collective (every lane of the warp calls it).
+// Returns true on penetration; dir points from obj1 to obj2.
 template <typename real>
-TB_NOINL bool mpr_penetration(const CObj<real>& o1, const CObj<real>& o2, real tol, int max_iter,
+TB_NOINL bool mpr_penetration(const CObj<real>& o1g, const CObj<real>& o2g, real tol, int max_iter, bool has,
                               real* depth, real* dir_out, real* pos_out) {
-  Supp<real> p[4], v4;
-  real dir[3], va[3], vb[3], dot, c2[3];
-  // ---- discoverPortal
-  obj_center(o1, p[0].v1); obj_center(o2, c2);
-  sub3(p[0].v, p[0].v1, c2);
-  if (ccd_vec_is_origin(p[0].v)) p[0].v[0] += Lim<real>::EPS * real(10);
-  scl3(dir, p[0].v, real(-1)); ccd_normalize(dir);
-  mink_support(o1, o2, dir, p[1]);
-  dot = dot3(p[1].v, dir);
-  if (ccd_is_zero(dot) || dot < 0) return false;
-  cross3(dir, p[0].v, p[1].v);
-  if (ccd_is_zero(dot3(dir, dir))) {
-    // origin on v1 (touching: depth 0, no direction -> MuJoCo drops it) or on the v0-v1 segment
-    if (ccd_vec_is_origin(p[1].v)) return false;
-    real v2[3];
-    sub3(v2, p[1].v1, p[1].v);
-    add3(pos_out, p[1].v1, v2); scl3(pos_out, pos_out, real(0.5));
-    copy3(dir_out, p[1].v); *depth = tsqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
-    return true;
+  enum { S1 = 0, S2, S3, S4, S5, DONE };
+  const CObj<real> o1 = o1g, o2 = o2g;
+  Supp<real> p0, p1, p2, p3, v4;
+  real dir[3] = {1, 0, 0}, c2[3] = {0, 0, 0};
+  int st = DONE, it = 0;
+  bool hit = false;
+  p0 = Supp<real>(); p1 = p0; p2 = p0; p3 = p0; v4 = p0;
+  if (has) {
+    obj_center(o1, p0.v1); obj_center(o2, c2);
+    sub3(p0.v, p0.v1, c2);
+    if (ccd_vec_is_origin(p0.v)) p0.v[0] += Lim<real>::EPS * real(10);
+    scl3(dir, p0.v, real(-1)); ccd_normalize(dir);
+    st = S1;
   }
-  ccd_normalize(dir);
-  mink_support(o1, o2, dir, p[2]);
-  dot = dot3(p[2].v, dir);
-  if (ccd_is_zero(dot) || dot < 0) return false;
-  sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
-  cross3(dir, va, vb); ccd_normalize(dir);
-  if (dot3(dir, p[0].v) > 0) { Supp<real> t = p[1]; p[1] = p[2]; p[2] = t; scl3(dir, dir, real(-1)); }
-  for (;;) {
-    bool cont = false;
-    mink_support(o1, o2, dir, p[3]);
-    dot = dot3(p[3].v, dir);
-    if (ccd_is_zero(dot) || dot < 0) return false;
-    cross3(va, p[1].v, p[3].v); dot = dot3(va, p[0].v);
-    if (dot < 0 && !ccd_is_zero(dot)) { p[2] = p[3]; cont = true; }
-    if (!cont) {
-      cross3(va, p[3].v, p[2].v); dot = dot3(va, p[0].v);
-      if (dot < 0 && !ccd_is_zero(dot)) { p[1] = p[3]; cont = true; }
-    }
-    if (!cont) break;
-    sub3(va, p[1].v, p[0].v); sub3(vb, p[2].v, p[0].v);
-    cross3(dir, va, vb); ccd_normalize(dir);
-  }
-  // ---- refinePortal
-  for (;;) {
-    portal_dir(p, dir);
-    dot = dot3(dir, p[1].v);
-    if (ccd_is_zero(dot) || dot > 0) break;
-    mink_support(o1, o2, dir, v4);
-    dot = dot3(v4.v, dir);
-    if (!(ccd_is_zero(dot) || dot > 0) || portal_reach_tol(p, v4, dir, tol)) return false;
-    expand_portal(p, v4);
-  }
-  // ---- findPenetr
-  for (int it = 0;; it++) {
-    portal_dir(p, dir);
-    mink_support(o1, o2, dir, v4);
-    if (portal_reach_tol(p, v4, dir, tol) || it > max_iter) {
-      real pdir[3];
-      *depth = tsqrt(tri_dist2_origin(p[1].v, p[2].v, p[3].v, pdir));
-      if (ccd_is_zero(pdir[0]) && ccd_is_zero(pdir[1]) && ccd_is_zero(pdir[2])) copy3(pdir, dir);
-      ccd_normalize(pdir);
-      copy3(dir_out, pdir);
-      // findPos: barycentric blend of the witness points
-      real vec[3], b[4], sum;
-      portal_dir(p, dir);
-      cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
-      cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
-      cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
-      cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
-      sum = b[0] + b[1] + b[2] + b[3];
-      if (ccd_is_zero(sum) || sum < 0) {
-        b[0] = 0;
-        cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
-        cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
-        cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
-        sum = b[1] + b[2] + b[3];
+  // after the portal is closed: refinement needs a support query only while the origin ray misses the portal
+  auto refine_check = [&]() {
+    portal_dir(p1, p2, p3, dir);
+    real dot = dot3(dir, p1.v);
+    if (ccd_is_zero(dot) || dot > 0) { it = 0; st = S5; }   // findPenetr starts with the same portal direction
+    else st = S4;
+  };
+  TB_UNROLL1
+  while (any(st != DONE)) {
+    Supp<real> s;
+    s = Supp<real>();
+    if (st != DONE) mink_support(o1, o2, dir, s);
+    if (st == S1) {
+      p1 = s;
+      real dot = dot3(p1.v, dir);
+      if (ccd_is_zero(dot) || dot < 0) st = DONE;
+      else {
+        cross3(dir, p0.v, p1.v);
+        if (ccd_is_zero(dot3(dir, dir))) {
+          // origin on v1 (touching: depth 0, no direction -> MuJoCo drops it) or on the v0-v1 segment
+          if (!ccd_vec_is_origin(p1.v)) {
+            real v2[3];
+            sub3(v2, p1.v1, p1.v);
+            add3(pos_out, p1.v1, v2); scl3(pos_out, pos_out, real(0.5));
+            copy3(dir_out, p1.v); *depth = tsqrt(dot3(dir_out, dir_out)); ccd_normalize(dir_out);
+            hit = true;
+          }
+          st = DONE;
+        } else { ccd_normalize(dir); st = S2; }
       }
-      real inv = trcp(sum), p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
-      // v0's second witness is obj2's centre
-      for (int i = 0; i < 4; i++) {
-        real v2[3];
-        if (i == 0) copy3(v2, c2); else sub3(v2, p[i].v1, p[i].v);
-        addscl3(p1, p[i].v1, b[i]); addscl3(p2, v2, b[i]);
+    } else if (st == S2) {
+      p2 = s;
+      real dot = dot3(p2.v, dir);
+      if (ccd_is_zero(dot) || dot < 0) st = DONE;
+      else {
+        real va[3], vb[3];
+        sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+        cross3(dir, va, vb); ccd_normalize(dir);
+        if (dot3(dir, p0.v) > 0) { Supp<real> t = p1; p1 = p2; p2 = t; scl3(dir, dir, real(-1)); }
+        st = S3;
       }
-      scl3(p1, p1, inv); scl3(p2, p2, inv);
-      add3(pos_out, p1, p2); scl3(pos_out, pos_out, real(0.5));
-      return true;
+    } else if (st == S3) {
+      p3 = s;
+      real dot = dot3(p3.v, dir);
+      if (ccd_is_zero(dot) || dot < 0) st = DONE;
+      else {
+        bool cont = false;
+        real va[3], vb[3];
+        cross3(va, p1.v, p3.v); dot = dot3(va, p0.v);
+        if (dot < 0 && !ccd_is_zero(dot)) { p2 = p3; cont = true; }
+        if (!cont) {
+          cross3(va, p3.v, p2.v); dot = dot3(va, p0.v);
+          if (dot < 0 && !ccd_is_zero(dot)) { p1 = p3; cont = true; }
+        }
+        if (cont) {
+          sub3(va, p1.v, p0.v); sub3(vb, p2.v, p0.v);
+          cross3(dir, va, vb); ccd_normalize(dir);
+        } else refine_check();
+      }
+    } else if (st == S4) {
+      v4 = s;
+      real dot = dot3(v4.v, dir);
+      if (!(ccd_is_zero(dot) || dot > 0) || portal_reach_tol(p1, p2, p3, v4, dir, tol)) st = DONE;
+      else { expand_portal(p0, p1, p2, p3, v4); refine_check(); }
+    } else if (st == S5) {
+      v4 = s;
+      if (portal_reach_tol(p1, p2, p3, v4, dir, tol) || it > max_iter) {
+        real pdir[3];
+        *depth = tsqrt(tri_dist2_origin(p1.v, p2.v, p3.v, pdir));
+        if (ccd_is_zero(pdir[0]) && ccd_is_zero(pdir[1]) && ccd_is_zero(pdir[2])) copy3(pdir, dir);
+        ccd_normalize(pdir);
+        copy3(dir_out, pdir);
+        // findPos: barycentric blend of the witness points
+        real vec[3], bb[4], sum;
+        portal_dir(p1, p2, p3, dir);
+        cross3(vec, p1.v, p2.v); bb[0] = dot3(vec, p3.v);
+        cross3(vec, p3.v, p2.v); bb[1] = dot3(vec, p0.v);
+        cross3(vec, p0.v, p1.v); bb[2] = dot3(vec, p3.v);
+        cross3(vec, p2.v, p1.v); bb[3] = dot3(vec, p0.v);
+        sum = bb[0] + bb[1] + bb[2] + bb[3];
+        if (ccd_is_zero(sum) || sum < 0) {
+          bb[0] = 0;
+          cross3(vec, p2.v, p3.v); bb[1] = dot3(vec, dir);
+          cross3(vec, p3.v, p1.v); bb[2] = dot3(vec, dir);
+          cross3(vec, p1.v, p2.v); bb[3] = dot3(vec, dir);
+          sum = bb[1] + bb[2] + bb[3];
+        }
+        real inv = trcp(sum), q1[3], q2[3], w2[3];
+        // v0's second witness is obj2's centre
+        scl3(q1, p0.v1, bb[0]); scl3(q2, c2, bb[0]);
+        addscl3(q1, p1.v1, bb[1]); sub3(w2, p1.v1, p1.v); addscl3(q2, w2, bb[1]);
+        addscl3(q1, p2.v1, bb[2]); sub3(w2, p2.v1, p2.v); addscl3(q2, w2, bb[2]);
+        addscl3(q1, p3.v1, bb[3]); sub3(w2, p3.v1, p3.v); addscl3(q2, w2, bb[3]);
+        scl3(q1, q1, inv); scl3(q2, q2, inv);
+        add3(pos_out, q1, q2); scl3(pos_out, pos_out, real(0.5));
+        hit = true;
+        st = DONE;
+      } else {
+        expand_portal(p0, p1, p2, p3, v4);
+        it++;
+        portal_dir(p1, p2, p3, dir);
+      }
     }
-    expand_portal(p, v4);
   }
+  return hit;
 }
 
 }  // namespace tb

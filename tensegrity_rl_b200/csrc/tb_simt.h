@@ -26,6 +26,7 @@ TB_FN int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 TB_FN bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 TB_FN unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 TB_FN void wsync() { __syncwarp(0xffffffffu); }
+TB_FN int lowbit(unsigned x) { return __ffs((int)x) - 1; }
 }  // namespace tb
 #else
 #define TB_DEV 0
@@ -46,5 +47,6 @@ TB_FN int shfl(int v, int src) { uint64_t b = (uint32_t)v; b = emu_shfl(b, src);
 TB_FN bool any(bool p) { return emu_ballot(p) != 0; }
 TB_FN unsigned ballot(bool p) { return emu_ballot(p); }
 TB_FN void wsync() { emu_sync(); }
+TB_FN int lowbit(unsigned x) { return __builtin_ffs((int)x) - 1; }
 }  // namespace tb
 #endif

@@ -21,6 +21,9 @@ using namespace tb;
 #ifndef TB_WARPS
 #define TB_WARPS 5
 #endif
+#ifndef TB_WARPS_SMALL
+#define TB_WARPS_SMALL 3   // second CTA shape of the step kernel, for batches that do not fill the machine with TB_WARPS
+#endif
 #ifndef TB_ALIGN
 #define TB_ALIGN 1
 #endif
@@ -36,15 +39,15 @@ template <typename real> __host__ __device__ constexpr size_t smem_model() { ret
 constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
 // env slices are spaced by an odd number of 16-byte units, so that the same field of the ten envs of a warp falls into different banks
 template <typename real> __host__ __device__ constexpr size_t envsh_stride() { return align16(sizeof(EnvSh<real>)) | 16; }
-template <typename real> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)TB_WARPS * EPW * envsh_stride<real>(); }
+template <typename real, int W> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)W * EPW * envsh_stride<real>(); }
 
 // Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every CTA pulls rounds of TB_WARPS chunks
 // (a chunk = EPW consecutive envs, or pool slots, stepped by one warp) from a global counter until the batch is done,
 // so rounds of different cost (contact count, Newton iterations, resets) balance dynamically.  The env rounds come
 // first, then the pool rounds, so that all warps of a CTA always run the same program.  The model constants are
 // staged once per CTA in shared memory.
-template <typename real, int MODE>
-__global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<real>* __restrict__ gm,
+template <typename real, int MODE, int W>
+__global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<real>* __restrict__ gm,
                                                                             const EnvCfg* __restrict__ gc, StepIO io,
                                                                             Con<real>* __restrict__ spill_base) {
   extern __shared__ __align__(16) unsigned char tb_smem[];
@@ -64,11 +67,11 @@ __global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(cons
   const int warp = threadIdx.x >> 5;
   EnvSh<real>& S = *reinterpret_cast<EnvSh<real>*>(tb_smem + smem_model<real>() + SMEM_CFG +
                                                    (size_t)(warp * EPW + L.grp) * envsh_stride<real>());
-  if (L.valid && L.bar == 0) S.spill = spill_base + (size_t)((blockIdx.x * TB_WARPS + warp) * EPW + L.grp) * (3 * KS);
+  if (L.valid && L.bar == 0) S.spill = spill_base + (size_t)((blockIdx.x * W + warp) * EPW + L.grp) * (3 * KS);
   __syncwarp();
-  const int env_chunks = (io.n_envs + EPW - 1) / EPW, env_rounds = (env_chunks + TB_WARPS - 1) / TB_WARPS;
+  const int env_chunks = (io.n_envs + EPW - 1) / EPW, env_rounds = (env_chunks + W - 1) / W;
   const int pool_chunks = (MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? (io.n_pool + EPW - 1) / EPW : 0;
-  const int pool_rounds = (pool_chunks + TB_WARPS - 1) / TB_WARPS;
+  const int pool_rounds = (pool_chunks + W - 1) / W;
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_round = atomicAdd(io.counter, 1);
@@ -76,11 +79,11 @@ __global__ void __launch_bounds__(TB_WARPS * 32, TB_MIN_CTAS) tb_env_kernel(cons
     const int round = s_round;
     if (round >= env_rounds + pool_rounds) break;
     if (round < env_rounds) {
-      const int first = (round * TB_WARPS + warp) * EPW;   // may lie beyond the batch: the warp then idles in step
+      const int first = (round * W + warp) * EPW;   // may lie beyond the batch: the warp then idles in step
       if (MODE == MODE_STEP) run_step(S, m, c, io, L, first, TB_ALIGN != 0);
       else if (MODE == MODE_RESET) run_reset(S, m, c, io, L, first);
       else run_forward(S, m, c, io, L, first);
-    } else run_pool(S, m, c, io, L, ((round - env_rounds) * TB_WARPS + warp) * EPW, MODE == MODE_RESET);
+    } else run_pool(S, m, c, io, L, ((round - env_rounds) * W + warp) * EPW, MODE == MODE_RESET);
   }
 }
 
@@ -186,7 +189,7 @@ struct TsgHandle {
   double* d_pool_obs; double* d_pool_real_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
   double* d_realobs_own;
-  int grid[3], regs;
+  int grid[3], grid_small, shape, regs;   // shape: 0 = TB_WARPS, 1 = TB_WARPS_SMALL warps per CTA in the step kernel
   size_t smem;
   cudaStream_t own_stream;
 };
@@ -212,14 +215,19 @@ static size_t extra_smem() {
   if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
   return (size_t)v;
 }
-template <typename real, int MODE>
-static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
+template <typename real, int MODE, int W>
+static int launch_w(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot, int grid) {
   io.counter = h->d_counter + counter_slot;
-  tb_env_kernel<real, MODE><<<h->grid[MODE], TB_WARPS * 32, smem_bytes<real>() + extra_smem(), s>>>(
+  tb_env_kernel<real, MODE, W><<<grid, W * 32, smem_bytes<real, W>() + extra_smem(), s>>>(
       (const ModelT<real>*)h->d_model, h->d_cfg, io, (Con<real>*)h->d_spill);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
+}
+template <typename real, int MODE>
+static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
+  if (MODE == MODE_STEP && h->shape == 1) return launch_w<real, MODE_STEP, TB_WARPS_SMALL>(h, io, s, counter_slot, h->grid_small);
+  return launch_w<real, MODE, TB_WARPS>(h, io, s, counter_slot, h->grid[MODE]);
 }
 // counter_slot: which of the handle's work counters the launch consumes (they are zeroed together, once per API call)
 template <int MODE>
@@ -230,23 +238,32 @@ static int zero_counters(TsgHandle* h, cudaStream_t s) {
   CK(cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), s));
   return 0;
 }
-template <typename real, int MODE>
-static int setup_kernel(TsgHandle* h, int num_sms) {
-  size_t smem = smem_bytes<real>() + extra_smem();
-  CK(cudaFuncSetAttribute(tb_env_kernel<real, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <typename real, int MODE, int W>
+static int setup_kernel(TsgHandle* h, int num_sms, int* grid) {
+  size_t smem = smem_bytes<real, W>() + extra_smem();
+  CK(cudaFuncSetAttribute(tb_env_kernel<real, MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<real, MODE>, TB_WARPS * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<real, MODE, W>, W * 32, smem));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
-  // what is not carved out for shared memory stays L1, which serves the lanes' local memory (contacts, spills)
-  int need = ((h->n_envs + EPW - 1) / EPW + TB_WARPS - 1) / TB_WARPS + ((h->n_pool + EPW - 1) / EPW + TB_WARPS - 1) / TB_WARPS;
+  // what is not carved out for shared memory stays L1, which serves the spilled contacts and the lanes' local memory
+  int need = ((h->n_envs + EPW - 1) / EPW + W - 1) / W + ((h->n_pool + EPW - 1) / EPW + W - 1) / W;
   int full = num_sms * per_sm;
-  h->grid[MODE] = need < full ? need : full;
-  if (MODE == MODE_STEP) {
+  *grid = need < full ? need : full;
+  if (MODE == MODE_STEP && (W == TB_WARPS) == (h->shape == 0)) {
     cudaFuncAttributes a;
-    CK(cudaFuncGetAttributes(&a, tb_env_kernel<real, MODE>));
+    CK(cudaFuncGetAttributes(&a, tb_env_kernel<real, MODE, W>));
     h->regs = a.numRegs; h->smem = smem;
   }
   return 0;
+}
+// CTA shape of the step kernel: a round (W chunks of EPW envs, one per warp) keeps an SM busy for about the same time
+// whatever W is (its warps run side by side), so the shape with fewer waves of rounds wins; the small shape's round is
+// ~15 % shorter (fewer envs wait for the slowest one at the alignment barriers)
+static int pick_shape(int n_envs, int num_sms) {
+  const char* e = getenv("TSG_SHAPE");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+  auto waves = [&](int w) { int rounds = ((n_envs + EPW - 1) / EPW + w - 1) / w; return (rounds + num_sms - 1) / num_sms; };
+  return waves(TB_WARPS_SMALL) * 0.85 < waves(TB_WARPS) * 1.0 ? 1 : 0;
 }
 template <typename real>
 static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
@@ -255,10 +272,13 @@ static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
   if (!err.empty()) FAIL("tsg_create: " + err);
   CK(cudaMalloc(&h->d_model, sizeof(dm)));
   CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
-  if (setup_kernel<real, MODE_STEP>(h, sms) || setup_kernel<real, MODE_RESET>(h, sms) || setup_kernel<real, MODE_FORWARD>(h, sms)) return -2;
+  h->shape = pick_shape(h->n_envs, sms);
+  if (setup_kernel<real, MODE_STEP, TB_WARPS>(h, sms, &h->grid[MODE_STEP]) || setup_kernel<real, MODE_STEP, TB_WARPS_SMALL>(h, sms, &h->grid_small) ||
+      setup_kernel<real, MODE_RESET, TB_WARPS>(h, sms, &h->grid[MODE_RESET]) || setup_kernel<real, MODE_FORWARD, TB_WARPS>(h, sms, &h->grid[MODE_FORWARD])) return -2;
   int gmax = h->grid[0] > h->grid[1] ? h->grid[0] : h->grid[1];
   if (h->grid[2] > gmax) gmax = h->grid[2];
-  CK(cudaMalloc(&h->d_spill, (size_t)gmax * TB_WARPS * EPW * (3 * KS) * sizeof(Con<real>)));   // contact slots beyond the shared-memory pool
+  size_t slots = (size_t)gmax * TB_WARPS > (size_t)h->grid_small * TB_WARPS_SMALL ? (size_t)gmax * TB_WARPS : (size_t)h->grid_small * TB_WARPS_SMALL;
+  CK(cudaMalloc(&h->d_spill, slots * EPW * (3 * KS) * sizeof(Con<real>)));   // contact slots beyond the shared-memory pool
   return 0;
 }
 
@@ -366,7 +386,7 @@ int tsg_pool_stats_host(TsgHandle* h, int* counts3) {
 }
 int tsg_kernel_config(const TsgHandle* h, int* warps_per_cta, int* smem_bytes_out, int* regs_per_thread) {
   if (!h) FAIL("tsg_kernel_config: null handle");
-  if (warps_per_cta) *warps_per_cta = TB_WARPS * 100 + G;  // warps per CTA * 100 + lanes per env
+  if (warps_per_cta) *warps_per_cta = (h->shape ? TB_WARPS_SMALL : TB_WARPS) * 100 + G;  // warps per CTA * 100 + lanes per env
   if (smem_bytes_out) *smem_bytes_out = (int)h->smem;
   if (regs_per_thread) *regs_per_thread = h->regs;
   return 0;

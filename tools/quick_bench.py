@@ -8,7 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 xml = sys.argv[3] if len(sys.argv) > 3 else "flat"
 check = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-env = TensegrityVecEnv(n, xml_file=xml, env="tr_env", auto_reset=bool(int(os.environ.get("TSG_AUTORESET", "1"))), reset_pool=os.environ.get("TSG_POOL", "auto") if os.environ.get("TSG_POOL", "auto") == "auto" else int(os.environ["TSG_POOL"]))
+env = TensegrityVecEnv(n, xml_file=xml, env="tr_env", precision=os.environ.get("TSG_PRECISION", "f64"), auto_reset=bool(int(os.environ.get("TSG_AUTORESET", "1"))), reset_pool=os.environ.get("TSG_POOL", "auto") if os.environ.get("TSG_POOL", "auto") == "auto" else int(os.environ["TSG_POOL"]))
 env.reset_tensor()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 ctrl = -0.45 + 0.3 * torch.rand(steps + 3, n, 6, generator=g, device="cuda", dtype=torch.float64)
