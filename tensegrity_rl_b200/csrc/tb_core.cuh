@@ -98,6 +98,9 @@ TB_FN int isum3(int v, int base) { return shfl(v, base) + shfl(v, base + 1) + sh
 TB_FN bool grp_any(bool p, int base) { return ((ballot(p) >> base) & 7u) != 0; }
 // loop conditions: uniform over the warp, or over the CTA when its warps run aligned (they then share fetched
 // instructions; every warp of the CTA executes the same sequence of these calls)
+#ifndef TB_ALIGN_LEVEL
+#define TB_ALIGN_LEVEL 2   // CTA barriers: 1 = substep entry, 2 = + top of every Newton iteration, 3 = + inside the iteration
+#endif
 TB_FN bool uni_any(bool p, bool aligned) {
 #if TB_DEV
   if (aligned) return __syncthreads_or(p ? 1 : 0) != 0;
@@ -886,7 +889,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   // ---------------- mj_fwdConstraint: warm-start choice + Newton
   bool act = pass_on && nact_env > 0;
   bool use_smooth = false;
-  if (uni_any(act, aligned)) {
+  if (uni_any(act, aligned && TB_ALIGN_LEVEL >= 3)) {
     wsync();
     real dw[6];
     for (int k = 0; k < 6; k++) dw[k] = B.warm[k] - asm_[k];
@@ -924,7 +927,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   bool first = true;
   TB_UNROLL1
   for (;;) {
-    if (!uni_any(act, aligned)) break;
+    if (!uni_any(act, aligned && TB_ALIGN_LEVEL >= 2)) break;
     // ---- forces at qacc (owners), then each bar lane gathers the wrenches of the contacts that touch its bar
     real cpart = 0;
     if (act && nmine > 0) {
@@ -964,7 +967,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     first = false;
     const bool go = act && iter < m.iterations;
     if (!go) act = false;
-    if (!uni_any(go, aligned)) break;
+    if (!uni_any(go, aligned && TB_ALIGN_LEVEL >= 3)) { if (TB_ALIGN_LEVEL == 2 && aligned) continue; else break; }
     // ---- Hessian: every bar lane builds its diagonal block from the contacts touching its bar, the owner of a
     // bar-bar contact the block below the diagonal; all into shared memory
     if (go) {
@@ -1009,7 +1012,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       for (int k = 0; k < 6; k++) x[k] = grad[k];
       if (indep) { blk_ldl(D[b], dinv + 6 * b); blk_fwd(D[b], x); }
       if (alone) { for (int k = 0; k < 6; k++) x[k] *= dinv[6 * b + k]; blk_bwd(D[b], x); }
-      if (uni_any(go && (c10 || c20 || c21), aligned)) {
+      if (uni_any(go && (c10 || c20 || c21), aligned && TB_ALIGN_LEVEL >= 3)) {
         if (go && b == 0 && !alone) for (int k = 0; k < 6; k++) xs[k] = x[k];   // z0
         wsync();
         if ((b == 1 && c10) || (b == 2 && c20)) blk_trsm(O[b - 1], D[0], dinv);
