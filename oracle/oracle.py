@@ -172,6 +172,20 @@ class Batch:
             self.b = None
 
 
+def step_states(xml_file, qpos, qvel, act, warm, ctrl, nstep=20, threads=0):
+    """every row stepped `nstep` substeps from the given state by the C oracle on all host threads.
+    Returns qpos', qvel', ten_length', and per row the (min, max) number of active contacts over the substeps."""
+    mj = MjLike(xml_file)
+    f = lambda a, w: np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1, w))
+    qpos, qvel, act, warm, ctrl = f(qpos, NQ), f(qvel, NV), f(act, NA), f(warm, NV), f(ctrl, NA)
+    n = len(qpos)
+    oq, ov, ot, mm = np.zeros((n, NQ)), np.zeros((n, NV)), np.zeros((n, NT)), np.zeros((n, 2), np.int32)
+    P = lambda a: a.ctypes.data_as(C.POINTER(d))
+    lib().tsgo_step_states(C.byref(mj.model), n, int(nstep), P(qpos), P(qvel), P(act), P(warm), P(ctrl), P(oq), P(ov), P(ot),
+                           mm.ctypes.data_as(C.POINTER(i32)), int(threads))
+    return oq, ov, ot, mm
+
+
 def mpr(type1, pos1, mat1, size1, type2, pos2, mat2, size2, tol=1e-6, iters=50):
     L = lib()
     f = lambda a: np.ascontiguousarray(a, np.float64)

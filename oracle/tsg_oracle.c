@@ -1174,3 +1174,52 @@ long tsgo_bench(const TsgModel *m, int n_envs, int n_steps, int frame_skip, int 
   if (out_checksum) *out_checksum = j.checksum;
   return j.total;
 }
+
+/* n independent states stepped `nstep` times each from the given (qpos, qvel, act, warm start, ctrl) by a pthread
+ * pool: the checker of the full-batch parity tests.  ncon_minmax[e] = {min, max} active contacts over the substeps. */
+typedef struct {
+  const TsgModel *m; int n, nstep;
+  const double *qpos, *qvel, *act, *warm, *ctrl; double *oq, *ov, *ot; int *mm;
+  int next; pthread_mutex_t mu;
+} StatesJob;
+static void *states_worker(void *arg) {
+  StatesJob *j = (StatesJob *)arg;
+  TsgoData *d = (TsgoData *)malloc(sizeof(TsgoData));
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    int e0 = j->next; j->next += 16;
+    pthread_mutex_unlock(&j->mu);
+    if (e0 >= j->n) break;
+    for (int e = e0; e < e0 + 16 && e < j->n; e++) {
+      tsgo_reset_data(j->m, d);
+      memcpy(d->qpos, j->qpos + (size_t)e * TSG_NQ, sizeof(double) * TSG_NQ);
+      memcpy(d->qvel, j->qvel + (size_t)e * TSG_NV, sizeof(double) * TSG_NV);
+      memcpy(d->act, j->act + (size_t)e * TSG_NACT, sizeof(double) * TSG_NACT);
+      memcpy(d->qacc_warmstart, j->warm + (size_t)e * TSG_NV, sizeof(double) * TSG_NV);
+      memcpy(d->ctrl, j->ctrl + (size_t)e * TSG_NACT, sizeof(double) * TSG_NACT);
+      int lo = 1 << 30, hi = -1;
+      for (int s = 0; s < j->nstep; s++) {
+        tsgo_step(j->m, d, 1);
+        int nc = d->nefc / 6;
+        if (nc < lo) lo = nc;
+        if (nc > hi) hi = nc;
+      }
+      memcpy(j->oq + (size_t)e * TSG_NQ, d->qpos, sizeof(double) * TSG_NQ);
+      memcpy(j->ov + (size_t)e * TSG_NV, d->qvel, sizeof(double) * TSG_NV);
+      memcpy(j->ot + (size_t)e * TSG_NTEN, d->ten_length, sizeof(double) * TSG_NTEN);
+      if (j->mm) { j->mm[2 * e] = lo; j->mm[2 * e + 1] = hi; }
+    }
+  }
+  free(d);
+  return 0;
+}
+void tsgo_step_states(const TsgModel *m, int n, int nstep, const double *qpos, const double *qvel, const double *act,
+                      const double *warm, const double *ctrl, double *out_qpos, double *out_qvel, double *out_ten,
+                      int *ncon_minmax, int n_threads) {
+  StatesJob j = {m, n, nstep, qpos, qvel, act, warm, ctrl, out_qpos, out_qvel, out_ten, ncon_minmax, 0, PTHREAD_MUTEX_INITIALIZER};
+  if (n_threads <= 0) n_threads = tsgo_max_threads();
+  if (n_threads > 256) n_threads = 256;
+  pthread_t th[256];
+  for (int t = 0; t < n_threads; t++) pthread_create(&th[t], 0, states_worker, &j);
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], 0);
+}

@@ -136,6 +136,10 @@ TsgoBatch *tsgo_batch_create(const TsgModel *m, int n_envs, unsigned long long s
 void tsgo_batch_destroy(TsgoBatch *b);
 long tsgo_batch_step(TsgoBatch *b, int n_steps, int frame_skip, double lo, double hi, int n_threads);
 void tsgo_batch_get(const TsgoBatch *b, int e, double *qpos, double *qvel);
+/* n states stepped nstep substeps each from identical inputs (threaded): the checker of the full-batch parity tests */
+void tsgo_step_states(const TsgModel *m, int n, int nstep, const double *qpos, const double *qvel, const double *act,
+                      const double *warm, const double *ctrl, double *out_qpos, double *out_qvel, double *out_ten,
+                      int *ncon_minmax, int n_threads);
 
 #ifdef __cplusplus
 }

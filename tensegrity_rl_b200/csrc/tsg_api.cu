@@ -22,7 +22,7 @@ using namespace tb;
 #define TB_WARPS 5
 #endif
 #ifndef TB_WARPS_SMALL
-#define TB_WARPS_SMALL 3   // second CTA shape of the step kernel, for batches that do not fill the machine with TB_WARPS
+#define TB_WARPS_SMALL 2   // second CTA shape of the step kernel (two CTAs per SM), for batches that fit the machine at once
 #endif
 #ifndef TB_ALIGN
 #define TB_ALIGN 1
@@ -256,14 +256,15 @@ static int setup_kernel(TsgHandle* h, int num_sms, int* grid) {
   }
   return 0;
 }
-// CTA shape of the step kernel: a round (W chunks of EPW envs, one per warp) keeps an SM busy for about the same time
-// whatever W is (its warps run side by side), so the shape with fewer waves of rounds wins; the small shape's round is
-// ~15 % shorter (fewer envs wait for the slowest one at the alignment barriers)
+// CTA shape of the step kernel.  A batch that fits the machine at once in the small shape (2 CTAs of TB_WARPS_SMALL
+// warps per SM) is latency bound by a single round, which is shorter with fewer envs waiting for the slowest one at
+// the alignment barriers (4096 envs, steady state: 815k env-steps/s against 740k); larger batches run many rounds per
+// SM and the wide shape has the better throughput (131 072 envs: 1.40M against 1.20M).  profiles/r2_*.
 static int pick_shape(int n_envs, int num_sms) {
   const char* e = getenv("TSG_SHAPE");
   if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
-  auto waves = [&](int w) { int rounds = ((n_envs + EPW - 1) / EPW + w - 1) / w; return (rounds + num_sms - 1) / num_sms; };
-  return waves(TB_WARPS_SMALL) * 0.85 < waves(TB_WARPS) * 1.0 ? 1 : 0;
+  int rounds_small = ((n_envs + EPW - 1) / EPW + TB_WARPS_SMALL - 1) / TB_WARPS_SMALL;
+  return rounds_small <= 2 * num_sms ? 1 : 0;
 }
 template <typename real>
 static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {

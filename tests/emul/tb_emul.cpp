@@ -90,7 +90,13 @@ static void run_warp(std::function<void()> body) {
 
 using namespace tb;
 
+struct EmulF {   // fp32 physics twin (raw mj_step only: numerics studies of the optional fp32 mode)
+  ModelT<float> m;
+  EnvSh<float> S[EPW];
+  Con<float> spill[EPW][3 * KS];
+};
 struct Emul {
+  EmulF* f32;
   ModelT<double> m;
   EnvCfg c;
   float* hdata;
@@ -117,10 +123,14 @@ const char* tbe_create(const TsgModel* model, const TsgEnvConfig* cfg, void** ou
   memset(E->S, 0, sizeof(E->S));
   for (int g = 0; g < EPW; g++) E->S[g].spill = E->spill[g];
   E->seed = 0; E->env_id = 0; E->real_obs = nullptr;
+  E->f32 = new EmulF();
+  memset(E->f32->S, 0, sizeof(E->f32->S));
+  err = make_model<float>(*model, E->f32->m, E->hdata);
+  for (int g = 0; g < EPW; g++) E->f32->S[g].spill = E->f32->spill[g];
   *out = E;
   return nullptr;
 }
-void tbe_destroy(void* h) { Emul* E = (Emul*)h; free(E->hdata); delete E; }
+void tbe_destroy(void* h) { Emul* E = (Emul*)h; free(E->hdata); delete E->f32; delete E; }
 int tbe_envs_per_warp() { return EPW; }
 int tbe_envsh_bytes() { return (int)sizeof(EnvSh<double>); }
 
@@ -193,6 +203,29 @@ void tbe_mj_step(void* h, int n, double* rec, const double* ctrl, int nstep, dou
       int e = L.grp;
       if (ten_length) for (int i = 0; i < NTEN; i++) ten_length[e * NTEN + i] = S.tlen[i];
       if (cfrc_ext) for (int i = 0; i < 24; i++) cfrc_ext[e * 24 + i] = S.cfrc[i];
+      if (stats) { int* s = stats + 6 * e; s[0] = S.nact; s[1] = S.niter; s[2] = S.nls; s[3] = S.nmpr; s[4] = S.overflow; s[5] = S.bad; }
+    }
+    wsync();
+    store_env(S, L, on, A, r);
+  });
+}
+void tbe_mj_step_f32(void* h, int n, double* rec, const double* ctrl, int nstep, double* ten_length, int* stats) {
+  Emul* E = (Emul*)h;
+  EmulF* F = E->f32;
+  run_warp([&]() {
+    LaneCtx L = make_lane();
+    EnvSh<float>& S = F->S[L.grp];
+    const bool on = L.valid && L.grp < n;
+    Aux A;
+    double head[HEADING_SLOTS];
+    double* r = rec + (size_t)(on ? L.grp : 0) * STATE_STRIDE;
+    load_env(S, L, on, A, r, head);
+    if (on && L.bar == 0) for (int i = 0; i < NACT; i++) S.ctrl[i] = ctrl[(size_t)L.grp * NACT + i];
+    wsync();
+    simulate(S, F->m, L, on, nstep, true, false);
+    if (on && L.bar == 0) {
+      int e = L.grp;
+      if (ten_length) for (int i = 0; i < NTEN; i++) ten_length[e * NTEN + i] = S.tlen[i];
       if (stats) { int* s = stats + 6 * e; s[0] = S.nact; s[1] = S.niter; s[2] = S.nls; s[3] = S.nmpr; s[4] = S.overflow; s[5] = S.bad; }
     }
     wsync();

@@ -76,29 +76,52 @@ CASES = [("flat", "tr_env", "straight"), ("flat", "tr_env", "turn"), ("flat", "t
 
 @pytest.mark.parametrize("xml,env,task", CASES)
 def test_env_semantics_parity(xml, env, task):
-    """reset (explicit draws) + steps: obs / reward / done / info against the numpy+C oracle env."""
+    """reset (explicit draws) + 50 steps of 64 envs: obs / reward / done / info against the numpy+C oracle env, every
+    env every step, at the north_star tolerance (1e-9; reward relative).  The oracle env steps from the CUDA path's
+    physics state of the previous step (qpos, qvel, act, warm start, ctrl -- single-step agreement, the dynamics being
+    chaotic) and keeps its own env bookkeeping (heading ring, waypoints, step counters, stale kinematics)."""
     import torch
     from oracle.envs import OracleEnv
-    n, ncheck = 64, 3
+    n = 64
     rng = np.random.default_rng(3)
     draws = np.concatenate([rng.uniform(0, 1, (n, 2)), rng.standard_normal((n, 6)), rng.uniform(0, 1, (n, 2))], 1)
     v = _vec(n, xml, env, desired_action=task, auto_reset=False)
     obs0 = v.reset_tensor(draws=draws).cpu().numpy()
-    oes = [OracleEnv(xml, env, desired_action=task) for _ in range(ncheck)]
-    for k, oe in enumerate(oes):
-        assert np.abs(oe.reset(draws[k]) - obs0[k]).max() < 1e-6
+    oes = [OracleEnv(xml, env, desired_action=task) for _ in range(n)]
+    # a reset is 1000+ substeps of free evolution from the pose table (on the height field: a 1 m drop and a bounce), i.e.
+    # long enough for rounding-level differences to grow in a few envs: the reset observation must agree to 1e-9 in the
+    # median and to 1e-6 in >= 85 % of the envs; the envs that drifted further apart leave the step comparison (their
+    # waypoints / reset headings, which derive from the reset pose, differ accordingly)
+    e0 = np.array([np.abs(oe.reset(draws[k]) - obs0[k]).max() for k, oe in enumerate(oes)])
+    print(xml, env, task, "reset obs error: median %.1e, within 1e-6: %d / %d" % (np.median(e0), int((e0 < 1e-6).sum()), n))
+    assert np.median(e0) < 1e-9 and (e0 < 1e-6).sum() >= 0.85 * n
     lo, hi = (-0.45, -0.15) if env == "tensegrity_env" else (-0.45, 0.15)
-    for st in range(10):
+    nbad = ncheck = 0
+    alive = e0 < 1e-6
+    for st in range(50):
         a = rng.uniform(lo, hi, (n, 6))
+        before = v.get_state()
         obs, rew, done = v.step_tensor(torch.as_tensor(a, device="cuda"))
         obs, rew, done, info = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), v.info.cpu().numpy()
         for k, oe in enumerate(oes):
+            if not alive[k]:
+                continue
+            mj = oe.mj
+            mj.qpos[:] = before["qpos"][k]; mj.qvel[:] = before["qvel"][k]; mj.act[:] = before["act"][k]
+            mj.qacc_warmstart[:] = before["qacc_warmstart"][k]; mj.ctrl[:] = before["ctrl"][k]
             o, r, term, trunc, inf = oe.step(a[k])
-            assert np.abs(o - obs[k]).max() < 1e-6
-            assert abs(r - rew[k]) <= 1e-6 * max(1.0, abs(r))
+            ncheck += 1
+            err = max(np.abs(o - obs[k]).max(), abs(r - rew[k]) / max(1.0, abs(r)))
+            if err > TOL:
+                nbad += 1
+                assert err < 1e-4, (st, k, err)     # an outlier is a contact that exists in one and not the other: small
             assert bool(done[k]) == (term or trunc)
-            assert info[k, 3] == pytest.approx(inf["x_position"], abs=1e-7)
-            assert info[k, 22] == pytest.approx(inf["total_bar_contact"], rel=1e-5, abs=1e-5)
+            assert info[k, 3] == pytest.approx(inf["x_position"], abs=1e-8)
+            assert info[k, 22] == pytest.approx(inf["total_bar_contact"], rel=1e-4, abs=1e-5)
+            if done[k]:
+                alive[k] = False          # no auto reset here: a finished env leaves the comparison
+    print(xml, env, task, "checked", ncheck, "outliers above 1e-9:", nbad)
+    assert ncheck > 1000 and nbad <= max(2, ncheck // 200), (nbad, ncheck)
     v.close()
 
 
@@ -464,3 +487,99 @@ def test_planar_equivariance_at_full_batch():
     ok = err <= 1e-8
     assert np.abs(ten_a - ten_b)[ok].max() < 1e-8
     A.close(); B.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xml,steps,budget", [("flat", 200, 0.001), ("uneven", 120, 0.006)])
+def test_full_batch_parity_every_env_every_step(oracle, xml, steps, budget):
+    """BASELINE configs[1] at full size: 4096 batched envs, random ctrl in [-0.45, -0.15], fp64; after EVERY step EVERY
+    env is re-stepped by the threaded C oracle from the identical (qpos, qvel, act, warm start, ctrl) and compared at
+    1e-9 relative on qpos / qvel / tendon length.  Outliers are budgeted (0.1 % flat, 0.6 % height field) and each one
+    must be explained by a contact whose existence flickers within the step: the oracle's active-contact count varies
+    over the 20 substeps (or differs from the CUDA path's final count) -- the states where a summation-order-level
+    difference decides whether a contact exists in a substep."""
+    import torch
+    n = 4096
+    v = _vec(n, xml, "tr_env", auto_reset=False, terminate_when_unhealthy=False, max_episode_steps=0)
+    v.reset_tensor()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    nbad = ncheck = unexplained = 0
+    worst_ok, worst_out = 0.0, 0.0
+    for step in range(steps):
+        a = -0.45 + 0.3 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+        before = v.get_state()
+        v.step_tensor(a)
+        after, info = v.get_state(), v.info.cpu().numpy()
+        oq, ov, ot, mm = oracle.step_states(xml, before["qpos"], before["qvel"], before["act"], before["qacc_warmstart"], after["ctrl"])
+        scale = lambda x: np.maximum(1.0, np.abs(x).max(axis=1))
+        err = np.maximum.reduce([np.abs(after["qpos"] - oq).max(1) / scale(oq), np.abs(after["qvel"] - ov).max(1) / scale(ov),
+                                 np.abs(info[:, 8:17] - ot).max(1) / scale(ot)])
+        bad = err > TOL
+        ncheck += n; nbad += int(bad.sum())
+        worst_ok = max(worst_ok, float(err[~bad].max())); worst_out = max(worst_out, float(err.max()))
+        flicker = (mm[:, 0] != mm[:, 1]) | (mm[:, 1] != info[:, 19].astype(int))
+        unexplained += int((bad & ~flicker).sum())
+        assert int(info[:, 28].sum()) == 0 and int(info[:, 29].sum()) == 0      # no contact overflow, no bad state
+    print(xml, "checked", ncheck, "outliers", nbad, "(%.4f %%)" % (100.0 * nbad / ncheck), "largest", worst_out,
+          "worst within tolerance", worst_ok, "outliers without a contact-count change", unexplained)
+    assert nbad <= budget * ncheck, (nbad, ncheck)
+    assert unexplained == 0
+    v.close()
+
+
+@pytest.mark.gpu
+def test_golden_last_obs_through_the_cuda_path():
+    """The `_last_obs` vectors the REFERENCE's MuJoCo runs stored in its checkpoints, through the CUDA path: the state
+    reconstructed from each vector (tests/golden_pose.py), written with tsg_set_state and passed through tsg_forward,
+    must come back as the golden vector itself -- cap positions, cap velocities (incl. the reference's body-frame
+    angular velocity quirk), tendon lengths, tracking vector and yaw; bar quaternions (scipy convention) and qvel for
+    the legacy env -- to 1e-12.  A golden check of kinematics, site / tendon tables, geom frames and _get_obs."""
+    import golden_pose as GP
+    for name in sorted(GP.G):
+        obs = np.array(GP.G[name]["last_obs"])
+        if GP.G[name]["obs_dim"] == 48:
+            v = _vec(1, "uneven", "tr_env", desired_action=GP.TASK_OF[name], auto_reset=False)
+            qpos, qvel, waypt, res = GP.state_from_tr_obs(obs, v.md)
+        else:
+            v = _vec(1, "uneven", "tensegrity_env", desired_action="straight", auto_reset=False)
+            qpos, qvel, res = GP.state_from_legacy_obs(obs, v.md)
+            waypt = None
+        assert res < 1e-12
+        v.set_state(qpos=qpos[None], qvel=qvel[None])
+        if waypt is not None:
+            rec = v.get_records()
+            rec[0, 73:75] = waypt
+            v.set_records(rec)
+        got = v.forward_tensor().cpu().numpy()[0]
+        n = len(obs)
+        if name in ("traj_ccw", "traj_cw"):
+            assert np.all(obs[45:48] == 0)    # written by an older revision of the env (see tests/test_golden_last_obs.py)
+            n = 45
+        if GP.G[name]["obs_dim"] == 39:
+            for b in range(3):
+                if np.dot(got[4 * b:4 * b + 4], obs[4 * b:4 * b + 4]) < 0:
+                    got[4 * b:4 * b + 4] *= -1
+        assert np.abs(got[:n] - obs[:n]).max() < 1e-12, (name, np.abs(got[:n] - obs[:n]).max())
+        v.close()
+
+
+@pytest.mark.gpu
+def test_tracking_checkpoint_reproduces_reference_training_statistics():
+    """models_traj/SAC_16525000_track.zip (tr_env `tracking`, the heading-reward path of BASELINE configs[3],
+    tr_env.py:425-459): its ep_info_buffer holds return 224 over 253 steps = 0.885 per step at training time.  Its
+    `_last_obs` fits the uneven XML's bar geometry (tests/test_golden_last_obs.py), so it is run on that geometry over a
+    flat floor.  (The two aiming checkpoints of models_traj carry zeros in the last three observation slots: they were
+    trained on an older revision of the env whose observation the committed tr_env.py cannot produce.)"""
+    import json, os
+    from tensegrity_rl_b200 import SacActor
+    from tensegrity_rl_b200.rollout import rollout
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "last_obs.json")))
+    ref = G["traj_track"]["ep_return_mean"] / G["traj_track"]["ep_len_mean"]
+    v = _vec(2048, "legacy_flat", "tr_env", desired_action="tracking", auto_reset=True, reset_pool=512)
+    v.reset_tensor()
+    s = rollout(v, SacActor("traj_track"), 600)
+    got, length = s["return_sum"] / s["length_sum"], s["length_sum"] / max(1.0, s["episodes"])
+    print("track: return/step ours %.3f reference %.3f | episode length ours %.0f reference %.0f"
+          % (got, ref, length, G["traj_track"]["ep_len_mean"]))
+    assert abs(got - ref) < 0.1 * abs(ref) + 0.01, (got, ref)
+    v.close()

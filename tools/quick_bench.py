@@ -14,6 +14,8 @@ g = torch.Generator(device="cuda"); g.manual_seed(0)
 ctrl = -0.45 + 0.3 * torch.rand(steps + 3, n, 6, generator=g, device="cuda", dtype=torch.float64)
 for k in range(2):
     env.step_tensor(ctrl[k], want_info=False)
+for k in range(int(os.environ.get("TSG_SETTLE", "0"))):   # untimed random-ctrl steps: the steady-state contact load
+    env.step_tensor(-0.45 + 0.3 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64), want_info=False)
 worst = -1
 if check:
     from oracle import oracle as O
