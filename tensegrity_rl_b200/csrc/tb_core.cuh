@@ -32,6 +32,12 @@ constexpr int NCS = 3 * KP; // the order in which contacts are summed never depe
 constexpr int MAXCL = KP + KS;   // contacts one lane can own (a bar lying flat on the floor: 14)
 constexpr int ZONE_TOP = 0, ZONE_BOTTOM = 1, ZONE_MIDDLE = 2;
 
+// Arithmetic of a build.  `real`: kinematics, tendons, collision, integration.  `sreal`: the constraint solver (contact
+// rows, Newton Hessian, line search) -- the contact stiffness spans 1e6 x the bar inertia, so the solve needs fp64 to
+// stay within 1e-4 of the reference (pure fp32 lands at 1e-3 .. 1e-2: measured with the emulator).
+struct P64 { typedef double real; typedef double sreal; };
+struct P32 { typedef float real; typedef double sreal; };   // the optional fp32 mode: fp32 geometry, fp64 solver
+
 // one contact.  Written by its owner lane; read by the lanes of the bars it touches.
 template <typename real>
 struct Con {
@@ -49,8 +55,10 @@ struct Con {
 };
 
 // per-env slice of shared memory
-template <typename real>
+template <typename P>
 struct EnvSh {
+  typedef typename P::real real;
+  typedef typename P::sreal sreal;
   // world-frame exchange, rewritten by every pass; xpos / xmat / sph / tlen double as the "stale" kinematics the
   // reference's observation reads (positions lag qpos by one substep)
   real xpos[9], xmat[27], sph[18], tlen[NTEN];
@@ -63,20 +71,20 @@ struct EnvSh {
     struct { double qpos[NQ], qvel[NV], warm[NV]; } home;   // env state between physics calls (HBM record precision)
     real site[NEND * 3];                                    // tendon end points (tendon stage)
     struct {                                                // Newton solver
-      real D[3][21];      // diagonal blocks, packed lower; after factorisation unit L below the diagonal, d on it
-      real O[3][36];      // blocks below the diagonal, full 6x6 row-major: pairs (1,0), (2,0), (2,1)
-      real dinv[NV];
-      real xv[NV];        // world-frame twists of the vector under J; during the solve: the block rows' partial solutions
+      sreal D[3][21];     // diagonal blocks, packed lower; after factorisation unit L below the diagonal, d on it
+      sreal O[3][36];     // blocks below the diagonal, full 6x6 row-major: pairs (1,0), (2,0), (2,1)
+      sreal dinv[NV];
+      sreal xv[NV];       // world-frame twists of the vector under J; during the solve: the block rows' partial solutions
     } sol;
   } u;
 #if TB_KP > 0
-  Con<real> con[NCS];
+  Con<sreal> con[NCS];
 #endif
-  Con<real>* spill;       // global memory: 3 * KS slots of this env-in-flight
+  Con<sreal>* spill;      // global memory: 3 * KS slots of this env-in-flight
   int ncl[3];             // contacts owned by each lane
   int cpl[3];             // which blocks below the diagonal exist (set by the pair owners)
   int nact, overflow, bad, niter, nls, nmpr;
-  real barforce;
+  sreal barforce;
   double action[NACT];    // env layer (lane 0 of the env)
 };
 
@@ -109,10 +117,10 @@ TB_FN bool uni_any(bool p, bool aligned) {
   return any(p);
 }
 
-template <typename real> struct BarState { real x[3], q[4], v[6], warm[6]; };
+template <typename P> struct BarState { typename P::real x[3], q[4], v[6]; typename P::sreal warm[6]; };
 
 // k-th contact of lane `owner`
-template <typename real> TB_FN Con<real>& con_of(EnvSh<real>& S, int owner, int k) {
+template <typename P> TB_FN Con<typename P::sreal>& con_of(EnvSh<P>& S, int owner, int k) {
 #if TB_KP > 0
   if (k < KP) return S.con[owner * KP + k];
 #endif
@@ -130,7 +138,9 @@ template <typename real> TB_FN void make_frame(real* f) {
   cross3(f + 6, f, f + 3);
 }
 // out = J x, x given as world-frame twists per bar (lin, world angular) in xv
-template <typename real> TB_FN void con_mulJ(const Con<real>& c, const real* xv, real* out) {
+template <typename real, typename V> TB_FN void con_mulJ(const Con<real>& c, const V* xvv, real* out) {
+  real xv[NV];
+  for (int k = 0; k < 6; k++) { xv[6 * c.b2 + k] = (real)xvv[6 * c.b2 + k]; if (c.b1 >= 0) xv[6 * c.b1 + k] = (real)xvv[6 * c.b1 + k]; }
   real rel[3], relw[3], t[3];
   const real* w2 = xv + 6 * c.b2 + 3;
   cross3(t, w2, c.r2);
@@ -145,10 +155,10 @@ template <typename real> TB_FN void con_mulJ(const Con<real>& c, const real* xv,
   }
   for (int a = 0; a < 3; a++) { out[a] = dot3(c.frame + 3 * a, rel); out[3 + a] = dot3(c.frame + 3 * a, relw); }
 }
-template <typename real> TB_FN real impedance(const ModelT<real>& m, real pos) {
+template <typename real, typename MR> TB_FN real impedance(const ModelT<MR>& m, real pos) {
   const real MINIMP = real(0.0001), MAXIMP = real(0.9999);
-  real d0 = clampr(m.solimp[0], MINIMP, MAXIMP), dw = clampr(m.solimp[1], MINIMP, MAXIMP);
-  real width = tmax(Lim<real>::MINVAL, m.solimp[2]), mid = clampr(m.solimp[3], MINIMP, MAXIMP), power = tmax(real(1), m.solimp[4]);
+  real d0 = clampr((real)m.solimp[0], MINIMP, MAXIMP), dw = clampr((real)m.solimp[1], MINIMP, MAXIMP);
+  real width = tmax(Lim<real>::MINVAL, (real)m.solimp[2]), mid = clampr((real)m.solimp[3], MINIMP, MAXIMP), power = tmax(real(1), (real)m.solimp[4]);
   if (d0 == dw || width <= Lim<real>::MINVAL) return real(0.5) * (d0 + dw);
   real x = tdiv(tabs(pos), width), y;
   if (x >= 1) return dw;
@@ -161,8 +171,8 @@ template <typename real> TB_FN real impedance(const ModelT<real>& m, real pos) {
 }
 // mj_constraintUpdate for one elliptic contact at jar (+ jv if addjv): returns its cost; full: also the contact force
 // as a world wrench, the zone and the Hessian weights
-template <typename real> TB_FN real con_update(Con<real>& c, const ModelT<real>& m, bool full, bool addjv) {
-  real ja[6], U[6], T = 0, mu = m.mu;
+template <typename real, typename MR> TB_FN real con_update(Con<real>& c, const ModelT<MR>& m, bool full, bool addjv) {
+  real ja[6], U[6], T = 0, mu = (real)m.mu;
   for (int j = 0; j < 6; j++) ja[j] = addjv ? c.jar[j] + c.jv[j] : c.jar[j];
   U[0] = ja[0] * mu;
   for (int j = 1; j < 6; j++) { U[j] = ja[j] * m.fr[j - 1]; T += U[j] * U[j]; }
@@ -211,8 +221,8 @@ template <typename real> TB_FN real con_update(Con<real>& c, const ModelT<real>&
   return cost;
 }
 // cost and its first two derivatives along the search direction at step a, for one contact
-template <typename real> TB_FN void con_ls(const Con<real>& k, const ModelT<real>& m, real a, real& cost, real& d0, real& d1) {
-  real mu = m.mu;
+template <typename real, typename MR> TB_FN void con_ls(const Con<real>& k, const ModelT<MR>& m, real a, real& cost, real& d0, real& d1) {
+  real mu = (real)m.mu;
   const real U0 = k.t.ls.U0, V0 = k.t.ls.V0, UU = k.t.ls.UU, UV = k.t.ls.UV, VV = k.t.ls.VV;
   real N = U0 + a * V0, Tsqr = UU + a * (2 * UV + a * VV);
   bool bottom = false;
@@ -241,8 +251,8 @@ template <typename real> TB_FN void con_ls(const Con<real>& k, const ModelT<real
 // w4 I + (w3 - w4) n n^T) in closed form, n = contact normal; a middle-zone cone adds the rank-one terms
 // ca a a^T - cb b b^T with b stored in the contact (world frame) and a = mu (n - b_lin, -b_ang).
 template <typename real> struct ConW { real wl0, wl1, wa3, wa4; };
-template <typename real> TB_FN ConW<real> con_weights(const Con<real>& c, const ModelT<real>& m) {
-  const real* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
+template <typename real, typename MR> TB_FN ConW<real> con_weights(const Con<real>& c, const ModelT<MR>& m) {
+  const MR* wt = m.wtab[c.zone == ZONE_MIDDLE ? 1 : 0];
   ConW<real> w;
   w.wl0 = c.t.h.wcoef * wt[0]; w.wl1 = c.t.h.wcoef * wt[1]; w.wa3 = c.t.h.wcoef * wt[3]; w.wa4 = c.t.h.wcoef * wt[4];
   return w;
@@ -266,7 +276,7 @@ template <typename real> TB_FN void rank1_gen(real* X, real w, const real* a, co
   }
 }
 // cone vectors of a side: u = T^T v = (v_lin, r x v_lin + v_ang) for v = a, b
-template <typename real> TB_FN void cone_side(const Con<real>& c, const ModelT<real>& m, const real* r, real* ua, real* ub) {
+template <typename real, typename MR> TB_FN void cone_side(const Con<real>& c, const ModelT<MR>& m, const real* r, real* ua, real* ub) {
   const real* n = c.frame;
   real al[3], aa[3], t[3];
   for (int k = 0; k < 3; k++) { al[k] = m.mu * (n[k] - c.t.h.bw[k]); aa[k] = -m.mu * c.t.h.bw[3 + k]; }
@@ -276,7 +286,7 @@ template <typename real> TB_FN void cone_side(const Con<real>& c, const ModelT<r
   for (int k = 0; k < 3; k++) { ub[k] = c.t.h.bw[k]; ub[3 + k] = t[k] + c.t.h.bw[3 + k]; }
 }
 // diagonal block of one side (r = contact point relative to the bar's centre): H (packed lower 6x6) += T^T K T
-template <typename real> TB_FN void side_hessian(const Con<real>& c, const ModelT<real>& m, const real* r, real* H) {
+template <typename real, typename MR> TB_FN void side_hessian(const Con<real>& c, const ModelT<MR>& m, const real* r, real* H) {
   const ConW<real> w = con_weights(c, m);
   const real* n = c.frame;
   const real dl = w.wl0 - w.wl1, da = w.wa3 - w.wa4;
@@ -307,7 +317,7 @@ template <typename real> TB_FN void side_hessian(const Con<real>& c, const Model
 }
 // block between the two bars of a bar-bar contact: X (6x6 row-major, rows = bar with offset rh, cols = bar with rl)
 // += -T_h^T K T_l   (the two sides enter J with opposite signs)
-template <typename real> TB_FN void cross_hessian(const Con<real>& c, const ModelT<real>& m, const real* rh, const real* rl, real* X) {
+template <typename real, typename MR> TB_FN void cross_hessian(const Con<real>& c, const ModelT<MR>& m, const real* rh, const real* rl, real* X) {
   const ConW<real> w = con_weights(c, m);
   const real* n = c.frame;
   const real dl = w.wl0 - w.wl1, da = w.wa3 - w.wa4;
@@ -537,28 +547,35 @@ TB_FN bool hf_above_top_plane(const CObj<real>& pr, int gtype, const real* pos, 
 }
 
 // stores a new active contact of this lane (dist >= 0 gives no rows: includemargin 0)
-template <typename real>
-TB_FN void add_contact(EnvSh<real>& S, int lane_bar, int& nmine, int b1, int b2, real dist, const real* pos, const real* normal) {
+template <typename P>
+TB_FN void add_contact(EnvSh<P>& S, int lane_bar, int& nmine, int b1, int b2, typename P::real dist, const typename P::real* pos,
+                       const typename P::real* normal) {
+  typedef typename P::sreal sreal;
   if (!(dist < 0)) return;
   if (nmine >= MAXCL) { S.overflow = 1; return; }
-  Con<real>& c = con_of(S, lane_bar, nmine++);
+  Con<sreal>& c = con_of(S, lane_bar, nmine++);
   c.b1 = b1; c.b2 = b2; c.owner = lane_bar;
-  copy3(c.frame, normal);
+  for (int k = 0; k < 3; k++) c.frame[k] = (sreal)normal[k];
   make_frame(c.frame);
-  sub3(c.r2, pos, S.xpos + 3 * b2);
-  if (b1 >= 0) sub3(c.r1, pos, S.xpos + 3 * b1); else { c.r1[0] = c.r1[1] = c.r1[2] = 0; }
-  c.D0 = dist;   // parked until the rows are built
+  for (int k = 0; k < 3; k++) {
+    c.r2[k] = (sreal)pos[k] - (sreal)S.xpos[3 * b2 + k];
+    c.r1[k] = b1 >= 0 ? (sreal)pos[k] - (sreal)S.xpos[3 * b1 + k] : sreal(0);
+  }
+  c.D0 = (sreal)dist;   // parked until the rows are built
 }
 
 // ------------------------------------------------------------------ one physics pass
 // mj_forward (integ = false) or mj_step (integ = true) for the envs of the warp that are `on`.  The bar state B is
 // the lane's registers; the env's contacts of the last pass stay in S on return.
-template <typename real>
-TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, bool integ, bool aligned) {
+template <typename P>
+TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, const LaneCtx& L, bool on, bool integ, bool aligned) {
+  typedef typename P::real real;
+  typedef typename P::sreal sreal;
   const int b = L.bar, base = L.base;
   const real MINV = Lim<real>::MINVAL;
+  const sreal SMINV = Lim<sreal>::MINVAL;
   const real* Mb = m.M + 6 * b;
-  real* const qacc = B.warm;   // the acceleration iterate starts from (and ends as) the warm start
+  sreal* const qacc = B.warm;   // the acceleration iterate starts from (and ends as) the warm start
   auto reset_data = [&]() {   // mj_resetData on this lane's bar
     for (int k = 0; k < 3; k++) B.x[k] = m.qpos0[7 * b + k];
     for (int k = 0; k < 4; k++) B.q[k] = m.qpos0[7 * b + 3 + k];
@@ -574,7 +591,8 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     if (bad && on) { if (b == 0) S.bad |= 1; reset_data(); }
     wsync();
   }
-  real R[9], asm_[6], Dblk[21], fcon[6], Iw[6];
+  real R[9], Dblk[21];
+  sreal Rs[9], asm_[6], fcon[6], Iw[6];
   bool pass_on = on;
   TB_UNROLL1
   for (int pass = 0; pass < 2; pass++) {
@@ -582,6 +600,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   if (pass_on) {
     normalize4(B.q);
     quat2mat(R, B.q);
+    for (int k = 0; k < 9; k++) Rs[k] = (sreal)R[k];
     for (int k = 0; k < 3; k++) { S.xpos[3 * b + k] = B.x[k]; S.vw[6 * b + k] = B.v[k]; }
     for (int k = 0; k < 9; k++) S.xmat[9 * b + k] = R[k];
     real ww[3];
@@ -648,29 +667,30 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     // qacc_smooth = M^-1 (passive + actuator - bias)
     const real* I = m.inertia[b];
     const real* w = B.v + 3;
-    real al[3];
+    sreal al[3];
     for (int k = 0; k < 3; k++) {
       int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-      asm_[k] = (f[k] + Mb[k] * m.grav[k]) * m.invM[6 * b + k];
-      al[k] = (f[3 + k] - (w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]))) * m.invM[6 * b + 3 + k];
+      asm_[k] = (sreal)((f[k] + Mb[k] * m.grav[k]) * m.invM[6 * b + k]);
+      al[k] = (sreal)((f[3 + k] - (w[k1] * (I[k2] * w[k2]) - w[k2] * (I[k1] * w[k1]))) * m.invM[6 * b + 3 + k]);
     }
     // from here to the end of the solve the bar's angular dofs are WORLD-frame components (the rotation is orthogonal,
     // so costs, norms and the Newton direction are the same as in body coordinates): qacc_smooth, the warm start /
     // iterate, and the rotational inertia R diag(I) R^T
-    mulMV(asm_ + 3, R, al);
-    mulMV(al, R, B.warm + 3);
+    mulMV(asm_ + 3, Rs, al);
+    mulMV(al, Rs, B.warm + 3);
     for (int k = 0; k < 3; k++) B.warm[3 + k] = al[k];
     for (int i = 0, e = 0; i < 3; i++)
-      for (int k = 0; k <= i; k++, e++) Iw[e] = R[3 * i] * I[0] * R[3 * k] + R[3 * i + 1] * I[1] * R[3 * k + 1] + R[3 * i + 2] * I[2] * R[3 * k + 2];
+      for (int k = 0; k <= i; k++, e++)
+        Iw[e] = Rs[3 * i] * (sreal)I[0] * Rs[3 * k] + Rs[3 * i + 1] * (sreal)I[1] * Rs[3 * k + 1] + Rs[3 * i + 2] * (sreal)I[2] * Rs[3 * k + 2];
   }
   wsync();   // the tendon end points are dead: their storage now carries the solver's exchange
   // publishes a per-bar 6-vector (a world-frame twist) for the contact owners
-  auto publish = [&](const real* a, bool doit) {
+  auto publish = [&](const sreal* a, bool doit) {
     if (doit) for (int k = 0; k < 6; k++) S.u.sol.xv[6 * b + k] = a[k];
   };
   // out = M_w d for this bar (mass on the linear part, world-frame rotational inertia on the angular part)
-  auto mulM = [&](const real* d, real* out) {
-    for (int k = 0; k < 3; k++) out[k] = Mb[k] * d[k];
+  auto mulM = [&](const sreal* d, sreal* out) {
+    for (int k = 0; k < 3; k++) out[k] = (sreal)Mb[k] * d[k];
     out[3] = Iw[0] * d[3] + Iw[1] * d[4] + Iw[3] * d[5];
     out[4] = Iw[1] * d[3] + Iw[2] * d[4] + Iw[4] * d[5];
     out[5] = Iw[3] * d[3] + Iw[4] * d[4] + Iw[5] * d[5];
@@ -752,19 +772,24 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       TB_UNROLL1
       while (any(cand != 0)) {
         const bool has = cand != 0;
-        CObj<real> o1, o2;
-        o1 = CObj<real>(); o2 = o1;
+        CObj<sreal> o1, o2;   // the narrow phase runs in the solver's precision: MPR's 1e-6 tolerance is out of fp32's reach
+        o1 = CObj<sreal>(); o2 = o1;
         if (has) {
           const int q = lowbit(cand);
           cand &= cand - 1;
+          CObj<real> pr;
+          hf_prism(m, rmin + q / per_row, cmin, q % per_row, pr);
           o1.type = 100;
-          hf_prism(m, rmin + q / per_row, cmin, q % per_row, o1);
-          o2.type = m.gtype[Gi]; copy3(o2.pos, pos); o2.size[0] = r; o2.size[1] = hl;
+          for (int k = 0; k < 3; k++) { o1.px[k] = pr.px[k]; o1.py[k] = pr.py[k]; o1.pz[k] = pr.pz[k]; }
+          o1.pbase = pr.pbase;
+          o2.type = m.gtype[Gi]; o2.size[0] = r; o2.size[1] = hl;
+          for (int k = 0; k < 3; k++) o2.pos[k] = pos[k];
           for (int k = 0; k < 9; k++) o2.R[k] = R[k];
           nmpr++;
         }
-        real depth = 0, dir[3] = {0, 0, 1}, cp[3] = {0, 0, 0};
-        bool hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, has, &depth, dir, cp);
+        sreal depthS = 0, dirS[3] = {0, 0, 1}, cpS[3] = {0, 0, 0};
+        bool hit = mpr_penetration(o1, o2, (sreal)m.mpr_tol, m.mpr_iterations, has, &depthS, dirS, cpS);
+        real depth = (real)depthS, dir[3] = {(real)dirS[0], (real)dirS[1], (real)dirS[2]}, cp[3] = {(real)cpS[0], (real)cpS[1], (real)cpS[2]};
         if (has) {
           if (hit && ccd_vec_is_origin(dir)) hit = false;
           if (hit) {
@@ -831,8 +856,8 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     while (any(cand != 0)) {
       const bool has = cand != 0;
       int cb1 = pb1, cb2 = pb2;
-      CObj<real> o1, o2;
-      o1 = CObj<real>(); o2 = o1;
+      CObj<sreal> o1, o2;
+      o1 = CObj<sreal>(); o2 = o1;
       if (has) {
         const int i = lowbit(cand);
         cand &= cand - 1;
@@ -848,12 +873,13 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         for (int k = 0; k < 3; k++) { o1.pos[k] = Xa[k] + Ra[3 * k + 2] * m.gz[g1]; o2.pos[k] = Xb[k] + Rb[3 * k + 2] * m.gz[g2]; }
         nmpr++;
       }
-      real depth = 0, nrm[3] = {1, 0, 0}, pos[3] = {0, 0, 0};
-      bool hit = mpr_penetration(o1, o2, m.mpr_tol, m.mpr_iterations, has, &depth, nrm, pos);
+      sreal depthS = 0, nrmS[3] = {1, 0, 0}, posS[3] = {0, 0, 0};
+      bool hit = mpr_penetration(o1, o2, (sreal)m.mpr_tol, m.mpr_iterations, has, &depthS, nrmS, posS);
+      real depth = (real)depthS, nrm[3] = {(real)nrmS[0], (real)nrmS[1], (real)nrmS[2]}, pos[3] = {(real)posS[0], (real)posS[1], (real)posS[2]};
       if (has) {
         if (hit && ccd_vec_is_origin(nrm)) hit = false;
         if (hit && (m.flags & 4u) && o1.type == GEOM_SPHERE) {
-          real nn[3]; sub3(nn, pos, o1.pos);
+          real nn[3] = {pos[0] - (real)o1.pos[0], pos[1] - (real)o1.pos[1], pos[2] - (real)o1.pos[2]};
           if (tsqrt(dot3(nn, nn)) > MINV) { normalize3(nn); copy3(nrm, nn); }
         }
         if (hit) add_contact(S, b, nmine, cb1, cb2, -depth, pos, nrm);
@@ -863,19 +889,19 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   if (pass_on) S.ncl[b] = nmine;
   wsync();
   // rows of this lane's contacts: velocity, impedance, reference acceleration, residual at qacc_smooth
-  real csm = 0;
+  sreal csm = 0;
   bool bbmine = false;   // does this lane own a bar-bar contact
   if (pass_on && nmine > 0) {
     TB_UNROLL1
     for (int s = 0; s < nmine; s++) {
-      Con<real>& c = con_of(S, b, s);
-      real dist = c.D0, vel[6], ja[6];
+      Con<sreal>& c = con_of(S, b, s);
+      sreal dist = c.D0, vel[6], ja[6];
       con_mulJ(c, S.vw, vel);
       con_mulJ(c, S.u.sol.xv, ja);
-      real imp = impedance(m, dist);
-      real tran = (c.b1 >= 0 ? m.invw_tran[c.b1] : real(0)) + m.invw_tran[c.b2];
-      c.D0 = trcp(tmax(MINV, tdiv(1 - imp, imp) * tran));
-      for (int r = 0; r < 6; r++) c.jar[r] = ja[r] - (-m.B * vel[r] - (r ? real(0) : m.K * imp * dist));
+      sreal imp = impedance(m, dist);
+      sreal tran = (c.b1 >= 0 ? (sreal)m.invw_tran[c.b1] : sreal(0)) + (sreal)m.invw_tran[c.b2];
+      c.D0 = trcp(tmax(SMINV, tdiv(1 - imp, imp) * tran));
+      for (int r = 0; r < 6; r++) c.jar[r] = ja[r] - (-(sreal)m.B * vel[r] - (r ? sreal(0) : (sreal)m.K * imp * dist));
       csm += con_update(c, m, false, false);
       if (c.b1 >= 0) bbmine = true;
     }
@@ -891,78 +917,78 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
   bool use_smooth = false;
   if (uni_any(act, aligned && TB_ALIGN_LEVEL >= 3)) {
     wsync();
-    real dw[6];
+    sreal dw[6];
     for (int k = 0; k < 6; k++) dw[k] = B.warm[k] - asm_[k];
     publish(dw, act);
     wsync();
-    real cws = 0;
+    sreal cws = 0;
     if (act) {
       if (nmine > 0) {
         TB_UNROLL1
         for (int s = 0; s < nmine; s++) {
-          Con<real>& c = con_of(S, b, s);
+          Con<sreal>& c = con_of(S, b, s);
           con_mulJ(c, S.u.sol.xv, c.jv);
           cws += con_update(c, m, false, true);
         }
       }
-      real md[6];
+      sreal md[6];
       mulM(dw, md);
-      for (int k = 0; k < 6; k++) cws += real(0.5) * md[k] * dw[k];
+      for (int k = 0; k < 6; k++) cws += sreal(0.5) * md[k] * dw[k];
     }
     csm = sum3(csm, base); cws = sum3(cws, base);
     use_smooth = cws > csm;
     if (act && !use_smooth && nmine > 0) {
       TB_UNROLL1
       for (int s = 0; s < nmine; s++) {
-        Con<real>& c = con_of(S, b, s);
+        Con<sreal>& c = con_of(S, b, s);
         for (int r = 0; r < 6; r++) c.jar[r] += c.jv[r];
       }
     }
   }
   if (pass_on) { if (!act || use_smooth) for (int k = 0; k < 6; k++) qacc[k] = asm_[k]; }
   for (int k = 0; k < 6; k++) fcon[k] = 0;
-  real grad[6], search[6] = {0, 0, 0, 0, 0, 0};
-  real cost = 0, oldcost = 0;
+  sreal grad[6], search[6] = {0, 0, 0, 0, 0, 0};
+  sreal cost = 0, oldcost = 0;
   int iter = 0, nls = 0;
   bool first = true;
   TB_UNROLL1
   for (;;) {
     if (!uni_any(act, aligned && TB_ALIGN_LEVEL >= 2)) break;
     // ---- forces at qacc (owners), then each bar lane gathers the wrenches of the contacts that touch its bar
-    real cpart = 0;
+    sreal cpart = 0;
     if (act && nmine > 0) {
       TB_UNROLL1
       for (int s = 0; s < nmine; s++) {
-        Con<real>& c = con_of(S, b, s);
+        Con<sreal>& c = con_of(S, b, s);
         cpart += con_update(c, m, true, false);
       }
     }
     wsync();
-    real gn = 0;
+    sreal gn = 0;
     if (act) {
-      real Fw[3] = {0, 0, 0}, Tw[3] = {0, 0, 0};
+      sreal Fw[3] = {0, 0, 0}, Tw[3] = {0, 0, 0};
       TB_UNROLL1
       for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
-        const Con<real>& c = con_of(S, o, s);
+        const Con<sreal>& c = con_of(S, o, s);
         if (c.zone == ZONE_TOP) continue;
-        real t[3];
+        sreal t[3];
         if (c.b2 == b) { cross3(t, c.r2, c.wr); for (int k = 0; k < 3; k++) { Fw[k] += c.wr[k]; Tw[k] += t[k] + c.wr[3 + k]; } }
         else if (c.b1 == b) { cross3(t, c.r1, c.wr); for (int k = 0; k < 3; k++) { Fw[k] -= c.wr[k]; Tw[k] -= t[k] + c.wr[3 + k]; } }
       }
       for (int k = 0; k < 3; k++) { fcon[k] = Fw[k]; fcon[3 + k] = Tw[k]; }
-      real d[6], md[6];
+      sreal d[6], md[6];
       for (int k = 0; k < 6; k++) d[k] = qacc[k] - asm_[k];
       mulM(d, md);
       for (int k = 0; k < 6; k++) {
-        cpart += real(0.5) * md[k] * d[k];
+        cpart += sreal(0.5) * md[k] * d[k];
         grad[k] = md[k] - fcon[k]; gn += grad[k] * grad[k];
       }
     }
-    real newcost = sum3(cpart, base);
+    sreal newcost = sum3(cpart, base);
     gn = sum3(gn, base);
     if (act) {
       oldcost = cost; cost = newcost;
-      if (!first && (m.solscale * (oldcost - cost) < m.tol || gn < m.gradtol * m.gradtol)) act = false;   // converged
+      if (!first && ((sreal)m.solscale * (oldcost - cost) < (sreal)m.tol || gn < (sreal)m.gradtol * (sreal)m.gradtol)) act = false;   // converged
     }
     first = false;
     const bool go = act && iter < m.iterations;
@@ -971,14 +997,14 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     // ---- Hessian: every bar lane builds its diagonal block from the contacts touching its bar, the owner of a
     // bar-bar contact the block below the diagonal; all into shared memory
     if (go) {
-      real H[21];
+      sreal H[21];
       for (int e = 0; e < 21; e++) H[e] = 0;
-      H[0] = H[2] = H[5] = Mb[0];
+      H[0] = H[2] = H[5] = (sreal)Mb[0];
       H[9] = Iw[0]; H[13] = Iw[1]; H[14] = Iw[2]; H[18] = Iw[3]; H[19] = Iw[4]; H[20] = Iw[5];
       S.cpl[b] = 0;
       TB_UNROLL1
       for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
-        const Con<real>& c = con_of(S, o, s);
+        const Con<sreal>& c = con_of(S, o, s);
         if (c.zone == ZONE_TOP) continue;
         if (c.b2 != b && c.b1 != b) continue;
         side_hessian(c, m, c.b2 == b ? c.r2 : c.r1, H);
@@ -986,12 +1012,12 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
       for (int e = 0; e < 21; e++) S.u.sol.D[b][e] = H[e];
       if (bbmine) {
         // this lane owns the pair p = b: rows = the higher bar, cols = the lower one
-        real X[36];
+        sreal X[36];
         for (int e = 0; e < 36; e++) X[e] = 0;
         bool anyx = false;
         TB_UNROLL1
         for (int s = 0; s < nmine; s++) {
-          const Con<real>& c = con_of(S, b, s);
+          const Con<sreal>& c = con_of(S, b, s);
           if (c.b1 < 0 || c.zone == ZONE_TOP) continue;
           if (c.b2 > c.b1) cross_hessian(c, m, c.r2, c.r1, X); else cross_hessian(c, m, c.r1, c.r2, X);
           anyx = true;
@@ -1005,10 +1031,10 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     {
       const bool c10 = go && S.cpl[0] != 0, c20 = go && S.cpl[1] != 0, c21in = go && S.cpl[2] != 0;
       const bool f21 = c10 && c20, c21 = c21in || f21;
-      real (*D)[21] = S.u.sol.D; real (*O)[36] = S.u.sol.O; real* dinv = S.u.sol.dinv; real* xs = S.u.sol.xv;
+      sreal (*D)[21] = S.u.sol.D; sreal (*O)[36] = S.u.sol.O; sreal* dinv = S.u.sol.dinv; sreal* xs = S.u.sol.xv;
       const bool indep = go && (b == 0 || (b == 1 && !c10) || (b == 2 && !c20 && !c21));   // no block left of the diagonal
       const bool alone = indep && ((b == 0 && !c10 && !c20) || (b == 1 && !c21) || b == 2);   // and none below it
-      real x[6];
+      sreal x[6];
       for (int k = 0; k < 6; k++) x[k] = grad[k];
       if (indep) { blk_ldl(D[b], dinv + 6 * b); blk_fwd(D[b], x); }
       if (alone) { for (int k = 0; k < 6; k++) x[k] *= dinv[6 * b + k]; blk_bwd(D[b], x); }
@@ -1060,17 +1086,17 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     // ---- exact line search along search: mj_solPrimal's bracketing search as a per-env state machine.  Every tick
     // evaluates cost / slope / curvature at ONE step size per env (3-lane sums), then each env advances its own
     // bracketing logic, so the envs of a warp stay in lock step whatever their individual search sequences are.
-    real snorm = 0, gs = 0, qG1 = 0, qG2 = 0, gauss = 0;
+    sreal snorm = 0, gs = 0, qG1 = 0, qG2 = 0, gauss = 0;
     if (go) {
-      real d[6], md[6], ms[6];
+      sreal d[6], md[6], ms[6];
       for (int k = 0; k < 6; k++) d[k] = qacc[k] - asm_[k];
       mulM(d, md); mulM(search, ms);
       for (int k = 0; k < 6; k++) {
-        real sk = search[k];
+        sreal sk = search[k];
         snorm += sk * sk; gs += grad[k] * sk;
         qG1 += sk * md[k];
-        qG2 += real(0.5) * sk * ms[k];
-        gauss += real(0.5) * md[k] * d[k];
+        qG2 += sreal(0.5) * sk * ms[k];
+        gauss += sreal(0.5) * md[k] * d[k];
       }
     }
     snorm = sum3(snorm, base); gs = sum3(gs, base);
@@ -1081,32 +1107,32 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     if (go && nmine > 0) {
       TB_UNROLL1
       for (int s = 0; s < nmine; s++) {
-        Con<real>& k = con_of(S, b, s);
+        Con<sreal>& k = con_of(S, b, s);
         con_mulJ(k, S.u.sol.xv, k.jv);
-        real q0 = 0, q1 = 0, q2 = 0, UU = 0, UV = 0, VV = 0;
+        sreal q0 = 0, q1 = 0, q2 = 0, UU = 0, UV = 0, VV = 0;
         for (int j = 0; j < 6; j++) {
-          real D = k.D0 * m.dscale[j], ja = k.jar[j], jv = k.jv[j];
-          q0 += real(0.5) * D * ja * ja; q1 += D * ja * jv; q2 += real(0.5) * D * jv * jv;
-          if (j > 0) { real U = ja * m.fr[j - 1], V = jv * m.fr[j - 1]; UU += U * U; UV += U * V; VV += V * V; }
+          sreal D = k.D0 * (sreal)m.dscale[j], ja = k.jar[j], jv = k.jv[j];
+          q0 += sreal(0.5) * D * ja * ja; q1 += D * ja * jv; q2 += sreal(0.5) * D * jv * jv;
+          if (j > 0) { sreal U = ja * (sreal)m.fr[j - 1], V = jv * (sreal)m.fr[j - 1]; UU += U * U; UV += U * V; VV += V * V; }
         }
         k.t.ls.q0 = q0; k.t.ls.q1 = q1; k.t.ls.q2 = q2;
-        k.t.ls.U0 = k.jar[0] * m.mu; k.t.ls.V0 = k.jv[0] * m.mu; k.t.ls.UU = UU; k.t.ls.UV = UV; k.t.ls.VV = VV;
+        k.t.ls.U0 = k.jar[0] * (sreal)m.mu; k.t.ls.V0 = k.jv[0] * (sreal)m.mu; k.t.ls.UU = UU; k.t.ls.UV = UV; k.t.ls.VV = VV;
       }
     }
-    real alpha = 0;
+    sreal alpha = 0;
     int evals = 1;
     {
-      struct Pnt { real alpha, cost, d0, d1; };
+      struct Pnt { sreal alpha, cost, d0, d1; };
       // W_*: waiting for the evaluation it requested; L_*: pure logic, resolved without an evaluation
       enum { W_P1 = 0, W_A, W_P1NEXT, W_MID, W_B1, W_B2, L_ACHECK, L_AFTERA, L_BCHECK, L_DOB2, L_ENDITER, L_FINAL, LS_DONE };
-      const real gtol = m.tol * m.ls_tol * snorm * (m.meaninertia * NV);
+      const sreal gtol = (sreal)m.tol * (sreal)m.ls_tol * snorm * ((sreal)m.meaninertia * NV);
       const int maxe = m.ls_iterations;
       Pnt p0, p1, p2, pmid, p1next, p2next, c0;
-      p0.alpha = 0; p0.cost = cost; p0.d0 = gs; p0.d1 = -gs > 0 ? -gs : MINV;   // alpha = 0 is analytic (H search = -grad)
+      p0.alpha = 0; p0.cost = cost; p0.d0 = gs; p0.d1 = -gs > 0 ? -gs : SMINV;   // alpha = 0 is analytic (H search = -grad)
       p1 = p2 = pmid = p1next = p2next = c0 = p0;
       int st = LS_DONE, dirn = 1;
       bool p2update = false, b1 = false, b2 = false;
-      real aeval = 0;
+      sreal aeval = 0;
       auto newton = [&](const Pnt& p) { return p.alpha - tdiv(p.d0, p.d1); };
       // update_bracket against the candidates captured at the mid-point evaluation: (old p1next = c0, p2next, pmid)
       auto bracket = [&](Pnt& p) {
@@ -1118,12 +1144,12 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         }
         return flag;
       };
-      if (go && !(snorm < MINV)) { st = W_P1; aeval = newton(p0); }
+      if (go && !(snorm < SMINV)) { st = W_P1; aeval = newton(p0); }
       TB_UNROLL1
       for (;;) {
         const bool ev = st != LS_DONE;
         if (!any(ev)) break;
-        real c_ = 0, d0_ = 0, d1_ = 0;
+        sreal c_ = 0, d0_ = 0, d1_ = 0;
         if (ev) {
           if (nmine > 0) {
             TB_UNROLL1
@@ -1133,7 +1159,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         }
         Pnt r;
         r.alpha = aeval; r.cost = sum3(c_, base); r.d0 = sum3(d0_, base); r.d1 = sum3(d1_, base);
-        if (r.d1 <= 0) r.d1 = MINV;
+        if (r.d1 <= 0) r.d1 = SMINV;
         if (ev) {
           evals++;
           switch (st) {
@@ -1152,7 +1178,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
               pmid = r;
               c0 = p1next;
               const Pnt* cand[3] = {&c0, &p2next, &pmid};
-              int best = -1; real bestcost = 0;
+              int best = -1; sreal bestcost = 0;
               for (int i = 0; i < 3; i++)
                 if (tabs(cand[i]->d0) < gtol && (best == -1 || cand[i]->cost < bestcost)) { bestcost = cand[i]->cost; best = i; }
               if (best >= 0) { alpha = cand[best]->alpha; st = LS_DONE; }
@@ -1175,7 +1201,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
               if (evals >= maxe || !p2update) { alpha = p1.alpha; st = LS_DONE; }
               else { p2next = p1; aeval = newton(p1); st = W_P1NEXT; }
             } else if (st == L_BCHECK) {
-              if (evals < maxe) { aeval = real(0.5) * (p1.alpha + p2.alpha); st = W_MID; } else st = L_FINAL;
+              if (evals < maxe) { aeval = sreal(0.5) * (p1.alpha + p2.alpha); st = W_MID; } else st = L_FINAL;
             } else if (st == L_DOB2) {
               b2 = bracket(p2) != 0;
               if (b2) { aeval = newton(p2); st = W_B2; } else st = L_ENDITER;
@@ -1200,7 +1226,7 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
         if (nmine > 0) {
           TB_UNROLL1
           for (int s = 0; s < nmine; s++) {
-            Con<real>& c = con_of(S, b, s);
+            Con<sreal>& c = con_of(S, b, s);
             for (int r = 0; r < 6; r++) c.jar[r] += alpha * c.jv[r];
           }
         }
@@ -1210,8 +1236,8 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     wsync();
   }
   if (pass_on) {   // the iterate back to body coordinates: it is the next warm start
-    real wl[3];
-    mulMTV(wl, R, qacc + 3);
+    sreal wl[3];
+    mulMTV(wl, Rs, qacc + 3);
     for (int k = 0; k < 3; k++) qacc[3 + k] = wl[k];
     if (nact_env > 0 && b == 0) { S.niter += iter; S.nls += nls; }
   }
@@ -1234,9 +1260,9 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
     real A[21], x[6];
     for (int e = 0; e < 21; e++) A[e] = -h * Dblk[e];
     {
-      real al[3], fl[3];
-      mulMTV(al, R, asm_ + 3); mulMTV(fl, R, fcon + 3);   // qacc_smooth and the constraint torque in body coordinates
-      for (int r = 0; r < 3; r++) { x[r] = Mb[r] * asm_[r] + fcon[r]; x[3 + r] = Mb[3 + r] * al[r] + fl[r]; }
+      sreal al[3], fl[3];
+      mulMTV(al, Rs, asm_ + 3); mulMTV(fl, Rs, fcon + 3);   // qacc_smooth and the constraint torque in body coordinates
+      for (int r = 0; r < 3; r++) { x[r] = (real)((sreal)Mb[r] * asm_[r] + fcon[r]); x[3 + r] = (real)((sreal)Mb[3 + r] * al[r] + fl[r]); }
     }
     for (int r = 0; r < 6; r++) A[r * (r + 1) / 2 + r] += Mb[r];
     TB_UNROLL
@@ -1288,25 +1314,28 @@ TB_FN void phys(BarState<real>& B, EnvSh<real>& S, const ModelT<real>& m, const 
 
 // mj_rnePostConstraint: cfrc_ext rows [torque; force] for world + 3 bars about the (stale) body positions, from the
 // contacts of the last pass; also the total bar-bar contact force magnitude (run.py:155-161).  Leaves S.cfrc.
-template <typename real>
-TB_FN void cfrc_stage(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on) {
+template <typename P>
+TB_FN void cfrc_stage(EnvSh<P>& S, const ModelT<typename P::real>& m, const LaneCtx& L, bool on) {
+  typedef typename P::real real;
+  typedef typename P::sreal sreal;
   const int b = L.bar, base = L.base;
-  real own[6] = {0, 0, 0, 0, 0, 0}, world[6] = {0, 0, 0, 0, 0, 0}, barf = 0;
+  sreal own[6] = {0, 0, 0, 0, 0, 0}, world[6] = {0, 0, 0, 0, 0, 0}, barf = 0;
   if (on && S.nact > 0) {
     // the world row is taken about the mass-weighted centre of the three bars
-    real com[3] = {0, 0, 0}, mt = 0;
-    for (int bb = 0; bb < NBAR; bb++) { addscl3(com, S.xpos + 3 * bb, m.M[6 * bb]); mt += m.M[6 * bb]; }
+    sreal com[3] = {0, 0, 0}, mt = 0;
+    for (int bb = 0; bb < NBAR; bb++) { for (int k = 0; k < 3; k++) com[k] += (sreal)S.xpos[3 * bb + k] * (sreal)m.M[6 * bb]; mt += (sreal)m.M[6 * bb]; }
     scl3(com, com, 1 / mt);
     for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
-      const Con<real>& c = con_of(S, o, s);
+      const Con<sreal>& c = con_of(S, o, s);
       if (c.zone == ZONE_TOP) continue;
-      real t[3];
+      sreal t[3];
       if (c.b2 == b) {
         cross3(t, c.r2, c.wr);
         for (int k = 0; k < 3; k++) { own[k] += t[k] + c.wr[3 + k]; own[3 + k] += c.wr[k]; }
         if (c.b1 < 0) {
-          real pos[3], r[3];
-          add3(pos, S.xpos + 3 * b, c.r2); sub3(r, pos, com); cross3(t, r, c.wr);
+          sreal r[3];
+          for (int k = 0; k < 3; k++) r[k] = (sreal)S.xpos[3 * b + k] + c.r2[k] - com[k];
+          cross3(t, r, c.wr);
           for (int k = 0; k < 3; k++) { world[k] -= t[k] + c.wr[3 + k]; world[3 + k] -= c.wr[k]; }
         }
       } else if (c.b1 == b) {
@@ -1319,8 +1348,8 @@ TB_FN void cfrc_stage(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, b
   for (int k = 0; k < 6; k++) world[k] = sum3(world[k], base);
   barf = sum3(barf, base);
   if (on) {
-    for (int k = 0; k < 6; k++) S.cfrc[6 * (b + 1) + k] = own[k];
-    if (b == 0) { for (int k = 0; k < 6; k++) S.cfrc[k] = world[k]; S.barforce = barf; }
+    for (int k = 0; k < 6; k++) S.cfrc[6 * (b + 1) + k] = (real)own[k];
+    if (b == 0) { for (int k = 0; k < 6; k++) S.cfrc[k] = (real)world[k]; S.barforce = barf; }
   }
   wsync();
 }

@@ -54,7 +54,7 @@ TB_FN double angle_normalize(double t) {  // tr_env.py:648-654
   return t;
 }
 // COM / left-right end-cap centroids from the (stale) kinematics of the last forward pass
-template <typename real> TB_FN void read_pose(const EnvSh<real>& S, Pose& P) {
+template <typename PR> TB_FN void read_pose(const EnvSh<PR>& S, Pose& P) {
   P.xy[0] = ((double)S.xpos[0] + (double)S.xpos[3] + (double)S.xpos[6]) / 3;
   P.xy[1] = ((double)S.xpos[1] + (double)S.xpos[4] + (double)S.xpos[7]) / 3;
   for (int k = 0; k < 3; k++) {
@@ -147,8 +147,8 @@ TB_NOINL void obs_noise(const EnvCfg& c, double* obs, unsigned long long seed, u
 }
 
 // observation (stale positions / tendon lengths, fresh qvel) -- lane 0
-template <typename real>
-TB_NOINL void compute_obs(const EnvSh<real>& S, const EnvCfg& c, const Aux& A, double* obs) {
+template <typename PR>
+TB_NOINL void compute_obs(const EnvSh<PR>& S, const EnvCfg& c, const Aux& A, double* obs) {
   if (c.env_kind == ENV_LEGACY) {
     for (int b = 0; b < 3; b++) {  // geom rXY: body frame with x, y columns negated (geom quat 0 0 0 1)
       double R[9];
@@ -185,13 +185,15 @@ TB_NOINL void compute_obs(const EnvSh<real>& S, const EnvCfg& c, const Aux& A, d
 
 // do_simulation(ctrl, nsub) (integ) or mj_forward (integ = false, nsub = 1) on the env state in S, then
 // mj_rnePostConstraint.  Warp-collective.  The bar state is register-resident for the whole call.
-template <typename real>
-TB_NOINL void simulate(EnvSh<real>& S, const ModelT<real>& m, const LaneCtx& L, bool on, int nsub, bool integ, bool aligned) {
-  BarState<real> B;
+template <typename PR>
+TB_NOINL void simulate(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const LaneCtx& L, bool on, int nsub, bool integ, bool aligned) {
+  typedef typename PR::real real;
+  typedef typename PR::sreal sreal;
+  BarState<PR> B;
   const int b = L.bar;
   for (int k = 0; k < 3; k++) B.x[k] = (real)S.u.home.qpos[7 * b + k];
   for (int k = 0; k < 4; k++) B.q[k] = (real)S.u.home.qpos[7 * b + 3 + k];
-  for (int k = 0; k < 6; k++) { B.v[k] = (real)S.u.home.qvel[6 * b + k]; B.warm[k] = (real)S.u.home.warm[6 * b + k]; }
+  for (int k = 0; k < 6; k++) { B.v[k] = (real)S.u.home.qvel[6 * b + k]; B.warm[k] = (sreal)S.u.home.warm[6 * b + k]; }
   wsync();
   TB_UNROLL1
   for (int s = 0; s < nsub; s++) {
@@ -218,8 +220,8 @@ TB_FN double heading_pop(Aux& A) {
 }
 
 // the part of env.step after do_simulation -- lane 0
-template <typename real>
-TB_NOINL void env_step_post(EnvSh<real>& S, const EnvCfg& c, Aux& A, StepOut& O) {
+template <typename PR>
+TB_NOINL void env_step_post(EnvSh<PR>& S, const EnvCfg& c, Aux& A, StepOut& O) {
   const double dt = c.dt;
   double xy_before[2] = {A.xy_prev[0], A.xy_prev[1]}, psi_before = A.psi_prev;
   Pose P; read_pose(S, P);
@@ -298,8 +300,8 @@ TB_NOINL void env_step_post(EnvSh<real>& S, const EnvCfg& c, Aux& A, StepOut& O)
 }
 
 // one env.step(action) with the action in S.action -- warp-collective; obs NOT computed here
-template <typename real>
-TB_FN void env_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A, StepOut& O, bool aligned) {
+template <typename PR>
+TB_FN void env_step(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A, StepOut& O, bool aligned) {
   const bool l0 = on && L.bar == 0;
   if (l0) {
     if (c.env_kind == ENV_TR) {  // _action_filter, k_FILTER = 1 (tr_env.py:680-683)
@@ -312,14 +314,14 @@ TB_FN void env_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
   wsync();
 }
 // refresh the "stale" pose bookkeeping after a forward pass (set_state) -- lane 0
-template <typename real> TB_FN void aux_from_forward(const EnvSh<real>& S, Aux& A) {
+template <typename PR> TB_FN void aux_from_forward(const EnvSh<PR>& S, Aux& A) {
   Pose P; read_pose(S, P);
   A.xy_prev[0] = P.xy[0]; A.xy_prev[1] = P.xy[1]; A.psi_prev = P.psi;
 }
 
 // env.reset() = MujocoEnv.reset (mj_resetData) + reset_model, in three pieces so that it can run either in one go
 // (tsg_reset) or one warm-up step per launch on a background pool slot.  Random draws: A.draws.
-template <typename real> TB_FN void reset_setpoints(EnvSh<real>& S, const EnvCfg& c, const Aux& A) {  // lane 0
+template <typename PR> TB_FN void reset_setpoints(EnvSh<PR>& S, const EnvCfg& c, const Aux& A) {  // lane 0
   const double* u = A.draws;
   for (int i = 0; i < NACT; i++) {
     double t = u[2 + i] * c.tendon_reset_stdev + c.tendon_reset_mean;
@@ -327,8 +329,8 @@ template <typename real> TB_FN void reset_setpoints(EnvSh<real>& S, const EnvCfg
     S.action[i] = t;
   }
 }
-template <typename real>
-TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
+template <typename PR>
+TB_FN void reset_begin(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   const bool l0 = on && L.bar == 0;
   const double* u = A.draws;
   int idx = 0;
@@ -371,16 +373,16 @@ TB_FN void reset_begin(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, c
   wsync();
 }
 // one of the warmup_steps settling steps at the set-points in S.action
-template <typename real>
-TB_FN void reset_warm_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
+template <typename PR>
+TB_FN void reset_warm_step(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   if (c.env_kind == ENV_TR) {   // do_simulation, no filter
     simulate(S, m, L, on, c.frame_skip, true, false);
     if (on && L.bar == 0) aux_from_forward(S, A);
     wsync();
   } else { StepOut O; env_step(S, m, c, L, on, A, O, false); }   // full self.step
 }
-template <typename real>
-TB_FN void reset_finish(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
+template <typename PR>
+TB_FN void reset_finish(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const LaneCtx& L, bool on, Aux& A) {
   if (on && L.bar == 0) {
     const double* u = A.draws;
     Pose P; read_pose(S, P);
@@ -412,7 +414,7 @@ TB_FN void reset_finish(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, 
 }
 
 // ---- state record <-> shared-memory home (the three lanes of the env split the 69 values)
-template <typename real> TB_FN void load_env(EnvSh<real>& S, const LaneCtx& L, bool on, Aux& A, const double* rec, double* head) {
+template <typename PR> TB_FN void load_env(EnvSh<PR>& S, const LaneCtx& L, bool on, Aux& A, const double* rec, double* head) {
   if (on) {
     for (int i = L.bar; i < SO_XY_PREV; i += G) {
       double v = rec[i];
@@ -435,7 +437,7 @@ template <typename real> TB_FN void load_env(EnvSh<real>& S, const LaneCtx& L, b
   }
   wsync();
 }
-template <typename real> TB_FN void store_env(const EnvSh<real>& S, const LaneCtx& L, bool on, const Aux& A, double* rec) {
+template <typename PR> TB_FN void store_env(const EnvSh<PR>& S, const LaneCtx& L, bool on, const Aux& A, double* rec) {
   if (!on) return;
   for (int i = L.bar; i < SO_XY_PREV; i += G) {
     double v;
@@ -478,8 +480,8 @@ TB_FN void make_draws(double* d, unsigned long long seed, unsigned long long env
 constexpr int OBS_MAX = 160;
 
 // ---- the step of EPW consecutive envs starting at `first` (one warp)
-template <typename real>
-TB_FN void run_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first, bool aligned) {
+template <typename PR>
+TB_FN void run_step(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first, bool aligned) {
   const int e = first + L.grp;
   const bool on = L.valid && e < io.n_envs, l0 = on && L.bar == 0;
   Aux A; StepOut O;
@@ -518,8 +520,8 @@ TB_FN void run_step(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
 }
 
 // ---- reset of the masked envs among EPW consecutive ones
-template <typename real>
-TB_FN void run_reset(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first) {
+template <typename PR>
+TB_FN void run_reset(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first) {
   const int e = first + L.grp;
   const bool on = L.valid && e < io.n_envs && (!io.mask || io.mask[e]), l0 = on && L.bar == 0;
   if (!any(on)) return;
@@ -556,8 +558,8 @@ TB_FN void run_reset(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, con
 // ---- background reset pool: slot p (record n_envs + p) advances by one warm-up step per launch until it holds a
 // completely reset env (state, heading ring, reset observation); tsg_assign_kernel then hands ready slots to envs
 // that are done.  phase (SO_FLAGS) = warm-up steps done, warmup_steps + 1 = ready.  finish_now: run to completion.
-template <typename real>
-TB_FN void run_pool(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first, bool finish_now) {
+template <typename PR>
+TB_FN void run_pool(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first, bool finish_now) {
   const int p = first + L.grp;
   const bool valid = L.valid && p < io.n_pool;
   const size_t row = (size_t)io.n_envs + (valid ? p : 0);
@@ -606,8 +608,8 @@ TB_FN void run_pool(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, cons
 }
 
 // ---- mj_forward on the stored state (after tsg_set_state): refresh kinematics bookkeeping and obs
-template <typename real>
-TB_FN void run_forward(EnvSh<real>& S, const ModelT<real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first) {
+template <typename PR>
+TB_FN void run_forward(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvCfg& c, const StepIO& io, const LaneCtx& L, int first) {
   const int e = first + L.grp;
   const bool on = L.valid && e < io.n_envs, l0 = on && L.bar == 0;
   Aux A;

@@ -35,21 +35,22 @@ static_assert(HEADING_SLOTS == TSG_HEADING_SLOTS, "heading slots");
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_FORWARD = 2 };
 
 __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-template <typename real> __host__ __device__ constexpr size_t smem_model() { return align16(sizeof(ModelT<real>)); }
+template <typename P> __host__ __device__ constexpr size_t smem_model() { return align16(sizeof(ModelT<typename P::real>)); }
 constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
 // env slices are spaced by an odd number of 16-byte units, so that the same field of the ten envs of a warp falls into different banks
-template <typename real> __host__ __device__ constexpr size_t envsh_stride() { return align16(sizeof(EnvSh<real>)) | 16; }
-template <typename real, int W> constexpr size_t smem_bytes() { return smem_model<real>() + SMEM_CFG + (size_t)W * EPW * envsh_stride<real>(); }
+template <typename P> __host__ __device__ constexpr size_t envsh_stride() { return align16(sizeof(EnvSh<P>)) | 16; }
+template <typename P, int W> constexpr size_t smem_bytes() { return smem_model<P>() + SMEM_CFG + (size_t)W * EPW * envsh_stride<P>(); }
 
 // Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every CTA pulls rounds of TB_WARPS chunks
 // (a chunk = EPW consecutive envs, or pool slots, stepped by one warp) from a global counter until the batch is done,
 // so rounds of different cost (contact count, Newton iterations, resets) balance dynamically.  The env rounds come
 // first, then the pool rounds, so that all warps of a CTA always run the same program.  The model constants are
 // staged once per CTA in shared memory.
-template <typename real, int MODE, int W>
-__global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<real>* __restrict__ gm,
+template <typename P, int MODE, int W>
+__global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<typename P::real>* __restrict__ gm,
                                                                             const EnvCfg* __restrict__ gc, StepIO io,
-                                                                            Con<real>* __restrict__ spill_base) {
+                                                                            Con<typename P::sreal>* __restrict__ spill_base) {
+  typedef typename P::real real;
   extern __shared__ __align__(16) unsigned char tb_smem[];
   __shared__ int s_round;
   {
@@ -57,16 +58,16 @@ __global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const Model
     uint32_t* dst = reinterpret_cast<uint32_t*>(tb_smem);
     for (int i = threadIdx.x; i < (int)(sizeof(ModelT<real>) / 4); i += blockDim.x) dst[i] = src[i];
     src = reinterpret_cast<const uint32_t*>(gc);
-    dst = reinterpret_cast<uint32_t*>(tb_smem + smem_model<real>());
+    dst = reinterpret_cast<uint32_t*>(tb_smem + smem_model<P>());
     for (int i = threadIdx.x; i < (int)(sizeof(EnvCfg) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   const ModelT<real>& m = *reinterpret_cast<const ModelT<real>*>(tb_smem);
-  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tb_smem + smem_model<real>());
+  const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tb_smem + smem_model<P>());
   const LaneCtx L = make_lane();
   const int warp = threadIdx.x >> 5;
-  EnvSh<real>& S = *reinterpret_cast<EnvSh<real>*>(tb_smem + smem_model<real>() + SMEM_CFG +
-                                                   (size_t)(warp * EPW + L.grp) * envsh_stride<real>());
+  EnvSh<P>& S = *reinterpret_cast<EnvSh<P>*>(tb_smem + smem_model<P>() + SMEM_CFG +
+                                                   (size_t)(warp * EPW + L.grp) * envsh_stride<P>());
   if (L.valid && L.bar == 0) S.spill = spill_base + (size_t)((blockIdx.x * W + warp) * EPW + L.grp) * (3 * KS);
   __syncwarp();
   const int env_chunks = (io.n_envs + EPW - 1) / EPW, env_rounds = (env_chunks + W - 1) / W;
@@ -215,35 +216,35 @@ static size_t extra_smem() {
   if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
   return (size_t)v;
 }
-template <typename real, int MODE, int W>
+template <typename P, int MODE, int W>
 static int launch_w(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot, int grid) {
   io.counter = h->d_counter + counter_slot;
-  tb_env_kernel<real, MODE, W><<<grid, W * 32, smem_bytes<real, W>() + extra_smem(), s>>>(
-      (const ModelT<real>*)h->d_model, h->d_cfg, io, (Con<real>*)h->d_spill);
+  tb_env_kernel<P, MODE, W><<<grid, W * 32, smem_bytes<P, W>() + extra_smem(), s>>>(
+      (const ModelT<typename P::real>*)h->d_model, h->d_cfg, io, (Con<typename P::sreal>*)h->d_spill);
   CK(cudaGetLastError());
   h->launches++;
   return 0;
 }
-template <typename real, int MODE>
+template <typename P, int MODE>
 static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
-  if (MODE == MODE_STEP && h->shape == 1) return launch_w<real, MODE_STEP, TB_WARPS_SMALL>(h, io, s, counter_slot, h->grid_small);
-  return launch_w<real, MODE, TB_WARPS>(h, io, s, counter_slot, h->grid[MODE]);
+  if (MODE == MODE_STEP && h->shape == 1) return launch_w<P, MODE_STEP, TB_WARPS_SMALL>(h, io, s, counter_slot, h->grid_small);
+  return launch_w<P, MODE, TB_WARPS>(h, io, s, counter_slot, h->grid[MODE]);
 }
 // counter_slot: which of the handle's work counters the launch consumes (they are zeroed together, once per API call)
 template <int MODE>
 static int launch_env(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
-  return h->precision == TSG_PRECISION_F32 ? launch_t<float, MODE>(h, io, s, counter_slot) : launch_t<double, MODE>(h, io, s, counter_slot);
+  return h->precision == TSG_PRECISION_F32 ? launch_t<P32, MODE>(h, io, s, counter_slot) : launch_t<P64, MODE>(h, io, s, counter_slot);
 }
 static int zero_counters(TsgHandle* h, cudaStream_t s) {
   CK(cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), s));
   return 0;
 }
-template <typename real, int MODE, int W>
+template <typename P, int MODE, int W>
 static int setup_kernel(TsgHandle* h, int num_sms, int* grid) {
-  size_t smem = smem_bytes<real, W>() + extra_smem();
-  CK(cudaFuncSetAttribute(tb_env_kernel<real, MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = smem_bytes<P, W>() + extra_smem();
+  CK(cudaFuncSetAttribute(tb_env_kernel<P, MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<real, MODE, W>, W * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<P, MODE, W>, W * 32, smem));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
   // what is not carved out for shared memory stays L1, which serves the spilled contacts and the lanes' local memory
   int need = ((h->n_envs + EPW - 1) / EPW + W - 1) / W + ((h->n_pool + EPW - 1) / EPW + W - 1) / W;
@@ -251,7 +252,7 @@ static int setup_kernel(TsgHandle* h, int num_sms, int* grid) {
   *grid = need < full ? need : full;
   if (MODE == MODE_STEP && (W == TB_WARPS) == (h->shape == 0)) {
     cudaFuncAttributes a;
-    CK(cudaFuncGetAttributes(&a, tb_env_kernel<real, MODE, W>));
+    CK(cudaFuncGetAttributes(&a, tb_env_kernel<P, MODE, W>));
     h->regs = a.numRegs; h->smem = smem;
   }
   return 0;
@@ -266,20 +267,20 @@ static int pick_shape(int n_envs, int num_sms) {
   int rounds_small = ((n_envs + EPW - 1) / EPW + TB_WARPS_SMALL - 1) / TB_WARPS_SMALL;
   return rounds_small <= 2 * num_sms ? 1 : 0;
 }
-template <typename real>
+template <typename P>
 static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
-  ModelT<real> dm;
-  std::string err = make_model<real>(*model, dm, h->d_hdata);
+  ModelT<typename P::real> dm;
+  std::string err = make_model<typename P::real>(*model, dm, h->d_hdata);
   if (!err.empty()) FAIL("tsg_create: " + err);
   CK(cudaMalloc(&h->d_model, sizeof(dm)));
   CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
   h->shape = pick_shape(h->n_envs, sms);
-  if (setup_kernel<real, MODE_STEP, TB_WARPS>(h, sms, &h->grid[MODE_STEP]) || setup_kernel<real, MODE_STEP, TB_WARPS_SMALL>(h, sms, &h->grid_small) ||
-      setup_kernel<real, MODE_RESET, TB_WARPS>(h, sms, &h->grid[MODE_RESET]) || setup_kernel<real, MODE_FORWARD, TB_WARPS>(h, sms, &h->grid[MODE_FORWARD])) return -2;
+  if (setup_kernel<P, MODE_STEP, TB_WARPS>(h, sms, &h->grid[MODE_STEP]) || setup_kernel<P, MODE_STEP, TB_WARPS_SMALL>(h, sms, &h->grid_small) ||
+      setup_kernel<P, MODE_RESET, TB_WARPS>(h, sms, &h->grid[MODE_RESET]) || setup_kernel<P, MODE_FORWARD, TB_WARPS>(h, sms, &h->grid[MODE_FORWARD])) return -2;
   int gmax = h->grid[0] > h->grid[1] ? h->grid[0] : h->grid[1];
   if (h->grid[2] > gmax) gmax = h->grid[2];
   size_t slots = (size_t)gmax * TB_WARPS > (size_t)h->grid_small * TB_WARPS_SMALL ? (size_t)gmax * TB_WARPS : (size_t)h->grid_small * TB_WARPS_SMALL;
-  CK(cudaMalloc(&h->d_spill, slots * EPW * (3 * KS) * sizeof(Con<real>)));   // contact slots beyond the shared-memory pool
+  CK(cudaMalloc(&h->d_spill, slots * EPW * (3 * KS) * sizeof(Con<typename P::sreal>)));   // contact slots beyond the shared-memory pool
   return 0;
 }
 
@@ -310,8 +311,8 @@ static int create_impl(TsgHandle* h, const TsgModel* model, const TsgEnvConfig* 
   CK(cudaMemset(h->d_heading, 0, n * HEADING_SLOTS * sizeof(double)));
   CK(cudaMemset(h->d_draws, 0, n * NDRAW * sizeof(double)));
   CK(cudaMemset(h->d_done, 0, n));
-  int rc = h->precision == TSG_PRECISION_F32 ? setup_model<float>(h, model, prop.multiProcessorCount)
-                                             : setup_model<double>(h, model, prop.multiProcessorCount);
+  int rc = h->precision == TSG_PRECISION_F32 ? setup_model<P32>(h, model, prop.multiProcessorCount)
+                                             : setup_model<P64>(h, model, prop.multiProcessorCount);
   if (rc) return rc;
   CK(cudaMalloc(&h->d_counter, 4 * sizeof(int)));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

@@ -72,6 +72,14 @@ class EmulWarp:
         self.L.tbe_mj_step(self.h, self.n, P(self.rec), P(c), int(nstep), P(ten), P(cfrc), P(stats, C.c_int))
         return ten, cfrc.reshape(self.n, 4, 6), stats
 
+    def mj_step_f32(self, ctrl, nstep=1):
+        """the same through the optional fp32 mode (fp32 kinematics / tendons / collision / integration, fp64 narrow
+        phase and constraint solver); the records stay fp64"""
+        ten = np.zeros((self.n, 9)); stats = np.zeros((self.n, 6), np.int32)
+        c = np.ascontiguousarray(np.broadcast_to(ctrl, (self.n, 6)), np.float64)
+        self.L.tbe_mj_step_f32(self.h, self.n, P(self.rec), P(c), int(nstep), P(ten), P(stats, C.c_int))
+        return ten, stats
+
     def step(self, action):
         a = np.ascontiguousarray(np.broadcast_to(action, (self.n, 6)), np.float64)
         rew = np.zeros(self.n); done = np.zeros(self.n, np.uint8)

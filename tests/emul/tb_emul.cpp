@@ -92,15 +92,15 @@ using namespace tb;
 
 struct EmulF {   // fp32 physics twin (raw mj_step only: numerics studies of the optional fp32 mode)
   ModelT<float> m;
-  EnvSh<float> S[EPW];
-  Con<float> spill[EPW][3 * KS];
+  EnvSh<P32> S[EPW];
+  Con<double> spill[EPW][3 * KS];
 };
 struct Emul {
   EmulF* f32;
   ModelT<double> m;
   EnvCfg c;
   float* hdata;
-  EnvSh<double> S[EPW];
+  EnvSh<P64> S[EPW];
   Con<double> spill[EPW][3 * KS];
   int counter;
   unsigned long long seed; long long env_id; double* real_obs;
@@ -132,7 +132,7 @@ const char* tbe_create(const TsgModel* model, const TsgEnvConfig* cfg, void** ou
 }
 void tbe_destroy(void* h) { Emul* E = (Emul*)h; free(E->hdata); delete E->f32; delete E; }
 int tbe_envs_per_warp() { return EPW; }
-int tbe_envsh_bytes() { return (int)sizeof(EnvSh<double>); }
+int tbe_envsh_bytes() { return (int)sizeof(EnvSh<P64>); }
 
 static StepIO make_io(int n, double* rec, double* heading, const Emul* E) {
   StepIO io;
@@ -190,7 +190,7 @@ void tbe_mj_step(void* h, int n, double* rec, const double* ctrl, int nstep, dou
   Emul* E = (Emul*)h;
   run_warp([&]() {
     LaneCtx L = make_lane();
-    EnvSh<double>& S = E->S[L.grp];
+    EnvSh<P64>& S = E->S[L.grp];
     const bool on = L.valid && L.grp < n;
     Aux A;
     double head[HEADING_SLOTS];
@@ -214,7 +214,7 @@ void tbe_mj_step_f32(void* h, int n, double* rec, const double* ctrl, int nstep,
   EmulF* F = E->f32;
   run_warp([&]() {
     LaneCtx L = make_lane();
-    EnvSh<float>& S = F->S[L.grp];
+    EnvSh<P32>& S = F->S[L.grp];
     const bool on = L.valid && L.grp < n;
     Aux A;
     double head[HEADING_SLOTS];

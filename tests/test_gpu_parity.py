@@ -583,3 +583,40 @@ def test_tracking_checkpoint_reproduces_reference_training_statistics():
           % (got, ref, length, G["traj_track"]["ep_len_mean"]))
     assert abs(got - ref) < 0.1 * abs(ref) + 0.01, (got, ref)
     v.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xml", ["flat", "uneven"])
+def test_fp32_mode_against_the_fp64_oracle(oracle, xml):
+    """The optional fp32 mode (TSG_PRECISION_F32: fp32 kinematics / tendons / collision / integration, fp64 narrow phase
+    and constraint solver) on BASELINE configs[1] inputs, flat and height field: 4096 envs, random ctrl; states are
+    produced by the fp64 path, handed to the fp32 handle and advanced by ONE mj_step (frame_skip 1), then compared with
+    the fp64 oracle from the identical state at the north_star tolerance of the mode, 1e-4 (qpos, qvel, tendon length).
+    A full env step (20 substeps) is checked at 1e-3."""
+    import torch
+    n = 4096
+    kw = dict(auto_reset=False, terminate_when_unhealthy=False, max_episode_steps=0)
+    v64 = _vec(n, xml, "tr_env", **kw)
+    v1 = _vec(n, xml, "tr_env", precision="f32", frame_skip=1, **kw)
+    v20 = _vec(n, xml, "tr_env", precision="f32", **kw)
+    v64.reset_tensor()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    rnd = lambda: -0.45 + 0.3 * torch.rand(n, 6, generator=g, device="cuda", dtype=torch.float64)
+    for rounds in range(4):
+        for _ in range(12 if xml == "flat" else 20):
+            v64.step_tensor(rnd())
+        st = v64.get_state()
+        a = rnd()
+        for v, nsub, tol in ((v1, 1, 1e-4), (v20, 20, 1e-3)):
+            v.set_state(qpos=st["qpos"], qvel=st["qvel"], act=st["act"], qacc_warmstart=st["qacc_warmstart"], ctrl=st["ctrl"])
+            v.step_tensor(a)
+            after, info = v.get_state(), v.info.cpu().numpy()
+            oq, ov, ot, mm = oracle.step_states(xml, st["qpos"], st["qvel"], st["act"], st["qacc_warmstart"], after["ctrl"], nstep=nsub)
+            scale = lambda x: np.maximum(1.0, np.abs(x).max(axis=1))
+            err = np.maximum.reduce([np.abs(after["qpos"] - oq).max(1) / scale(oq), np.abs(after["qvel"] - ov).max(1) / scale(ov),
+                                     np.abs(info[:, 8:17] - ot).max(1) / scale(ot)])
+            print(xml, "fp32 mode, %d substep(s): median %.1e  99.5%% %.1e  max %.1e" % (nsub, np.median(err), np.quantile(err, 0.995), err.max()))
+            assert np.quantile(err, 0.995) < tol and np.median(err) < 0.2 * tol
+            assert int(info[:, 28].sum()) == 0 and int(info[:, 29].sum()) == 0
+    for v in (v64, v1, v20):
+        v.close()
