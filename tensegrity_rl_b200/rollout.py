@@ -192,3 +192,71 @@ def run_test(env, actor, saved_data_dir, simulation_seconds=30, deterministic=Fa
     for k, v in rows.items():
         np.save(os.path.join(saved_data_dir, k + "_data.npy"), np.array(v))
     return {k: np.array(v) for k, v in rows.items()}
+
+
+def run_test3(env, track, ccw, cw, saved_data_dir, simulation_seconds=30, deterministic=False, env_index=0, waypoints=None):
+    """run.py `test3` (:192-310) for one env of a batch (`tr_env` aiming, is_test=True): the 3-policy waypoint loop
+    and its four files -- waypt_data.npy (the waypoint list), x_pos_data.npy / y_pos_data.npy (position after every
+    policy step), del_yaw_data.npy (heading error before every policy step).  As in the reference the `env.step(
+    tendon_loop_init)` taken at each new waypoint is neither counted nor recorded."""
+    import torch
+    os.makedirs(saved_data_dir, exist_ok=True)
+    I, e = _lib.INFO, env_index
+    env.reset_tensor()
+    ctl = WaypointController(env, track, ccw, cw, waypoints=waypoints, deterministic=deterministic)
+    xs, ys, dyaw = [], [], []
+    counter, extra, iters = 0, 500, int(simulation_seconds / env.dt)
+    while counter < iters and extra >= 0 and not bool(ctl.finished[e]):
+        hold = bool(ctl.hold[e])
+        a = ctl.action(env.obs)
+        obs, rew, done = env.step_tensor(a, want_info=True, auto_reset=False)
+        ctl.after_step(env.info)
+        if hold:
+            continue
+        inf = env.info[e].cpu().numpy()
+        dyaw.append(float(ctl.del_yaw[e])); xs.append(inf[I["x"]]); ys.append(inf[I["y"]])
+        counter += 1
+        if bool(done[e]):
+            extra -= 1
+    out = {"waypt": ctl.wp.cpu().numpy(), "x_pos": np.array(xs), "y_pos": np.array(ys), "del_yaw": np.array(dyaw)}
+    for k, v in out.items():
+        np.save(os.path.join(saved_data_dir, k + "_data.npy"), v)
+    return out
+
+
+def run_tracking_test(env, actor, saved_data_dir, simulation_seconds=30, episode_num=10, deterministic=False):
+    """run.py `tracking_test` (:312-365): `episode_num` tracking episodes, here run side by side on the first
+    `episode_num` envs of the batch, and its three files -- waypt_data.npy, xy_pos_data.npy, oripoint_data.npy, all
+    relative to the episode's origin point and rotated so that the waypoint lies on the +x axis.  An episode that is
+    done keeps stepping for up to 500 more steps without a reset, as in the reference; what is recorded is the info of
+    the last step the reference loop would have executed."""
+    import torch
+    os.makedirs(saved_data_dir, exist_ok=True)
+    I, n = _lib.INFO, episode_num
+    if env.num_envs < n:
+        raise ValueError("run_tracking_test needs num_envs >= episode_num (one episode per env)")
+    env.reset_tensor()
+    dev = env.device
+    extra = torch.full((n,), 500, dtype=torch.long, device=dev)
+    running = torch.ones(n, dtype=torch.bool, device=dev)
+    last = torch.zeros(n, 6, dtype=torch.float64, device=dev)   # oripoint (2), waypt (2), xy (2)
+    for _ in range(int(simulation_seconds / env.dt)):
+        a = actor(env.obs32, deterministic)
+        obs, rew, done = env.step_tensor(a.double(), want_info=True, auto_reset=False)
+        inf = env.info[:n]
+        row = torch.cat([inf[:, I["ori"]:I["ori"] + 2], inf[:, I["waypt"]:I["waypt"] + 2], inf[:, I["x"]:I["x"] + 1], inf[:, I["y"]:I["y"] + 1]], 1)
+        last = torch.where(running[:, None], row, last)
+        extra = extra - (done[:n].bool() & running).long()
+        running = running & (extra >= 0)
+        if not bool(running.any()):
+            break
+    last = last.cpu().numpy()
+    ori, way, xy = last[:, 0:2], last[:, 2:4] - last[:, 0:2], last[:, 4:6] - last[:, 0:2]
+    for i in range(n):
+        ang = np.arctan2(way[i, 1], way[i, 0])
+        rot = np.array([[np.cos(ang), np.sin(ang)], [np.sin(ang), -np.cos(ang)]])
+        way[i], xy[i] = rot @ way[i], rot @ xy[i]
+    out = {"waypt": way, "xy_pos": xy, "oripoint": ori - ori}
+    for k, v in out.items():
+        np.save(os.path.join(saved_data_dir, k + "_data.npy"), v)
+    return out

@@ -113,9 +113,9 @@ def test_oracle_env_reproduces_golden_observation(name):
                 got[4 * b:4 * b + 4] *= -1
     n = len(obs)
     if name in ("traj_ccw", "traj_cw"):
-        # these two checkpoints store (0, 0, 0) in the last three slots: written by an older revision of the env (the
-        # committed tr_env.py:626-639 cannot produce a zero tracking vector: its yaw would be NaN); the 45 physical
-        # components are compared
+        # these two checkpoints store (0, 0, 0) in the last three slots: the turn policies are fed zeros there
+        # (run.py test3 :262-272 blanks obs[45:48] before model_ccw / model_cw.predict), which the committed
+        # tr_env.py:626-639 itself cannot produce (a zero tracking vector has a NaN yaw); the 45 physical components are compared
         assert np.all(obs[45:48] == 0)
         n = 45
     assert np.abs(got[:n] - obs[:n]).max() < 1e-12
