@@ -150,6 +150,15 @@ typedef struct TsgEnvConfig {
   int32_t pad_noise_;
   double obs_noise_tendon_stdev;  /* 0.02 */
   double obs_noise_cap_pos_stdev; /* 0.05: end-cap positions AND end-cap velocities (tr_env.py:606-617) */
+  /* reset noise (tr_env.py:734-743, tensegrity_env.py:436-445): qpos += U(-s, s) per component, qvel = s * N(0, 1);
+   * off (0) in the reference defaults.  Draws: Philox(seed, env id, reset count), reproducible */
+  double reset_noise_scale;
+  /* contact cost (tr_env.py:292-304, 513-516): reward -= weight * sum(clip(cfrc_ext, range)^2) over the 4 x 6 external
+   * contact wrench rows, and info["reward_ctrl"] = -contact_cost; off in the reference defaults */
+  int32_t use_contact_forces;
+  int32_t pad_contact_;
+  double contact_cost_weight;     /* 5e-4 */
+  double contact_force_range[2];  /* (-1, 1); (-1000, 1000) for desired_action "turn" (tr_env.py:255-256) */
 } TsgEnvConfig;
 
 /* draws consumed by one reset (reference: unseeded numpy, tr_env.py:730,775,802-804,831-832) */

@@ -192,7 +192,13 @@ class OracleEnv:
             terminated = True
         if np.any(mj.cfrc_ext > c.kill_force) or np.any(mj.cfrc_ext < -c.kill_force):
             terminated = True
-        reward = fwd + healthy - ctrl_cost
+        costs, info_ctrl = ctrl_cost, -ctrl_cost
+        if c.use_contact_forces:   # tr_env.py:292-304, 513-516
+            lo, hi = c.contact_force_range[0], c.contact_force_range[1]
+            contact_cost = c.contact_cost_weight * np.sum(np.square(np.clip(mj.cfrc_ext, lo, hi)))
+            costs += contact_cost
+            info_ctrl = -contact_cost
+        reward = fwd + healthy - costs
         self.step_num += 1
         obs = self.get_obs()
         truncated = False
@@ -200,20 +206,24 @@ class OracleEnv:
             self.elapsed += 1
             truncated = c.max_episode_steps > 0 and self.elapsed >= c.max_episode_steps
         barforce = sum(np.linalg.norm(mj.contact_force(i)[:3]) for i, k in enumerate(mj.contacts()) if k.geom1 != 0)
-        info = dict(reward_forward=fwd, reward_ctrl=-ctrl_cost, reward_survive=healthy, x_position=xy1[0],
+        info = dict(reward_forward=fwd, reward_ctrl=info_ctrl, reward_survive=healthy, x_position=xy1[0],
                     y_position=xy1[1], psi=psi_info, x_velocity=self.xvel, y_velocity=self.yvel,
                     tendon_length=mj.ten_length.copy(), total_bar_contact=barforce,
                     max_cfrc=float(np.abs(mj.cfrc_ext).max()))
         return obs, float(reward), bool(terminated), bool(truncated), info
 
     # ---- reset
-    def reset(self, draws):
+    def reset(self, draws, noise=None):
+        """noise: (21 uniform(-1, 1) values, 18 standard normals) for reset_noise_scale (tr_env.py:734-743)"""
         c, mj = self.cfg, self.mj
         u = np.asarray(draws, np.float64)
         mj.reset_data()
         idx = min(max(int(np.floor(u[0] * c.npose)), 0), c.npose - 1)
         qpos = self.poses[idx].copy()
         qvel = np.zeros(18)
+        if c.reset_noise_scale > 0:
+            qpos = qpos + c.reset_noise_scale * np.asarray(noise[0])
+            qvel = c.reset_noise_scale * np.asarray(noise[1])
         if not self.legacy:
             mj.set_state(qpos, qvel)
         if (not self.legacy and self.task in ("turn", "tracking", "aiming")) or (self.legacy and self.task == "turn"):

@@ -16,9 +16,10 @@ struct Aux {  // env bookkeeping (valid in lane 0 of the env)
   int head_n, head_pos;
   double* heading;  // [HEADING_SLOTS] in global memory
   const double* draws;  // [NDRAW] in global memory: the random draws of the env's current reset
+  unsigned long long nz_seed, nz_stream, nz_nreset;   // keys of the reset-noise draws
 };
 struct StepOut {
-  double reward, fwd, ctrl_cost, healthy, psi, xy[2];
+  double reward, fwd, ctrl_cost, info_ctrl, healthy, psi, xy[2];   // info_ctrl: what info["reward_ctrl"] reports
   int terminated;
   double maxcfrc, barforce;
 };
@@ -110,6 +111,14 @@ TB_FN void philox(unsigned long long seed, unsigned long long ctr_lo, unsigned l
 TB_FN double u01(uint32_t a, uint32_t b) {  // 53-bit uniform in [0,1)
   unsigned long long x = (((unsigned long long)a << 32) | b) >> 11;
   return (double)x * (1.0 / 9007199254740992.0);
+}
+// reset noise (tr_env.py:734-743): component i of the 21 uniform qpos offsets (i < 21) / 18 normal qvel values, unscaled
+TB_FN double reset_noise_draw(unsigned long long seed, unsigned long long stream, unsigned long long nreset, int i) {
+  uint32_t r[4];
+  philox(seed ^ 0x72657365746e7365ull, stream, (nreset << 8) | (unsigned long long)i, r);
+  if (i < NQ) return 2.0 * u01(r[0], r[1]) - 1.0;
+  double u1 = 1.0 - u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+  return sqrt(-2.0 * log(u1)) * cos(2 * PI * u2);
 }
 // the pr-th pair of standard normals of one observation (Philox + Box-Muller)
 TB_FN void noise_pair(unsigned long long seed, unsigned long long stream, unsigned long long nreset,
@@ -291,7 +300,15 @@ TB_NOINL void env_step_post(EnvSh<PR>& S, const EnvCfg& c, Aux& A, StepOut& O) {
   double maxc = 0;
   for (int i = 0; i < 24; i++) maxc = fmax(maxc, fabs((double)S.cfrc[i]));
   if (maxc > c.kill_force) terminated = true;  // tr_env.py:480-481
-  O.reward = fwd + healthy - ctrl_cost;
+  double costs = ctrl_cost, info_ctrl = -ctrl_cost;
+  if (c.use_contact_forces) {   // tr_env.py:292-304, 513-516
+    double cs = 0;
+    for (int i = 0; i < 24; i++) { double f = fmin(c.contact_force_range[1], fmax(c.contact_force_range[0], (double)S.cfrc[i])); cs += f * f; }
+    cs *= c.contact_cost_weight;
+    costs += cs; info_ctrl = -cs;
+  }
+  O.reward = fwd + healthy - costs;
+  O.info_ctrl = info_ctrl;
   O.fwd = fwd; O.ctrl_cost = ctrl_cost; O.healthy = healthy; O.psi = psi_info;
   O.xy[0] = P.xy[0]; O.xy[1] = P.xy[1];
   O.terminated = terminated ? 1 : 0; O.maxcfrc = maxc; O.barforce = (double)S.barforce;
@@ -342,6 +359,10 @@ TB_FN void reset_begin(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const E
     if (idx > c.npose - 1) idx = c.npose - 1;
     if (idx < 0) idx = 0;
     for (int i = 0; i < NQ; i++) S.u.home.qpos[i] = c.reset_pose[idx][i];
+    if (c.reset_noise_scale > 0) {
+      for (int i = 0; i < NQ; i++) S.u.home.qpos[i] += c.reset_noise_scale * reset_noise_draw(A.nz_seed, A.nz_stream, A.nz_nreset, i);
+      for (int i = 0; i < NV; i++) S.u.home.qvel[i] = c.reset_noise_scale * reset_noise_draw(A.nz_seed, A.nz_stream, A.nz_nreset, NQ + i);
+    }
   }
   wsync();
   bool extra_set_state = (c.env_kind == ENV_TR) ? (c.task == TASK_TURN || c.task == TASK_TRACKING || c.task == TASK_AIMING)
@@ -355,7 +376,10 @@ TB_FN void reset_begin(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const E
     double ct = cos(theta), st = sin(theta), ch = cos(0.5 * theta), sh = sin(0.5 * theta);
     for (int b = 0; b < NBAR; b++) {
       double p[7];
-      for (int k = 0; k < 7; k++) p[k] = c.reset_pose[idx][7 * b + k];
+      for (int k = 0; k < 7; k++) {
+        p[k] = c.reset_pose[idx][7 * b + k];
+        if (c.reset_noise_scale > 0) p[k] += c.reset_noise_scale * reset_noise_draw(A.nz_seed, A.nz_stream, A.nz_nreset, 7 * b + k);
+      }
       double* q = S.u.home.qpos + 7 * b;
       q[0] = ct * p[0] - st * p[1]; q[1] = st * p[0] + ct * p[1]; q[2] = p[2];
       double n = sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5] + p[6] * p[6]);
@@ -505,7 +529,7 @@ TB_FN void run_step(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvC
     if (io.info) {
       double* I = io.info + (size_t)e * INFO_DIM;
       for (int i = 0; i < INFO_DIM; i++) I[i] = 0;
-      I[IO_REW_FWD] = O.fwd; I[IO_REW_CTRL] = -O.ctrl_cost; I[IO_REW_SURVIVE] = O.healthy;
+      I[IO_REW_FWD] = O.fwd; I[IO_REW_CTRL] = O.info_ctrl; I[IO_REW_SURVIVE] = O.healthy;
       I[IO_X] = O.xy[0]; I[IO_Y] = O.xy[1]; I[IO_PSI] = O.psi; I[IO_XVEL] = A.xvel; I[IO_YVEL] = A.yvel;
       for (int i = 0; i < 9; i++) I[IO_TEN + i] = (double)S.tlen[i];
       I[IO_TERMINATED] = O.terminated; I[IO_TRUNCATED] = truncated;
@@ -535,6 +559,7 @@ TB_FN void run_reset(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const Env
     double* dr = io.draws + (size_t)e * NDRAW;
     if (!io.explicit_draws) make_draws(dr, io.seed, (unsigned long long)(io.env_id_base + e), (unsigned long long)nreset);
     A.draws = dr;
+    A.nz_seed = io.seed; A.nz_stream = (unsigned long long)(io.env_id_base + e); A.nz_nreset = (unsigned long long)nreset;
   }
   wsync();
   reset_begin(S, m, c, L, on, A);
@@ -575,6 +600,7 @@ TB_FN void run_pool(EnvSh<PR>& S, const ModelT<typename PR::real>& m, const EnvC
     double* dr = io.draws + row * NDRAW;
     if (phase == 0) make_draws(dr, io.seed, (1ull << 40) + (unsigned long long)(io.env_id_base + p), (unsigned long long)nreset);
     A.draws = dr;
+    A.nz_seed = io.seed; A.nz_stream = (1ull << 40) + (unsigned long long)(io.env_id_base + p); A.nz_nreset = (unsigned long long)nreset;
   }
   wsync();
   const bool begin = on && phase == 0;

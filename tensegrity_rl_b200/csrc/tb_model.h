@@ -204,6 +204,11 @@ inline std::string make_env_cfg(const TsgEnvConfig& t, const TsgModel& mod, EnvC
   c.obs_noise_tendon_stdev = t.obs_noise_tendon_stdev; c.obs_noise_cap_pos_stdev = t.obs_noise_cap_pos_stdev;
   if (c.use_obs_noise && c.env_kind != ENV_TR) return "use_obs_noise exists for tr_env only";
   if (c.use_obs_noise && (c.obs_noise_tendon_stdev < 0 || c.obs_noise_cap_pos_stdev < 0)) return "negative obs noise stdev";
+  c.reset_noise_scale = t.reset_noise_scale;
+  if (!(c.reset_noise_scale >= 0)) return "negative reset_noise_scale";
+  c.use_contact_forces = t.use_contact_forces ? 1 : 0;
+  c.contact_cost_weight = t.contact_cost_weight;
+  c.contact_force_range[0] = t.contact_force_range[0]; c.contact_force_range[1] = t.contact_force_range[1];
   c.dt = mod.timestep * t.frame_skip;
   for (int p = 0; p < TSG_NPOSE; p++) for (int k = 0; k < NQ; k++) c.reset_pose[p][k] = t.reset_pose[p][k];
   return "";

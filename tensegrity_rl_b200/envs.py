@@ -60,17 +60,12 @@ class _SingleEnv:
     def __init__(self, xml_file=os.path.join(os.getcwd(), "3prism_jonathan_steady_side.xml"), device=0, seed=0,
                  max_episode_steps=0, render_mode=None, **kwargs):
         self.L = _lib.load()
-        for k in ("width", "height", "camera_id", "camera_name", "use_contact_forces", "contact_cost_weight",
-                  "contact_force_range", "reset_noise_scale", "contact_with_self_penalty",
+        for k in ("width", "height", "camera_id", "camera_name", "contact_with_self_penalty",
                   "use_cap_size_noise", "cap_size_noise_range", "threshold_waypt"):
             v = kwargs.pop(k, None)
             if k == "use_cap_size_noise" and v:   # tr_env.py:685-706 calls model.geom_names / geom_name2id, which the
                 # `mujoco` 2.3.7 bindings do not have (mujoco-py API): the reference itself raises AttributeError here
                 raise NotImplementedError("use_cap_size_noise=True fails in the reference too (mujoco-py-only API, tr_env.py:689-699)")
-            if k == "use_contact_forces" and v:
-                raise NotImplementedError(f"{k}=True is off in the reference defaults and not built (SURVEY 8f rank 4)")
-            if k == "reset_noise_scale" and v:
-                raise NotImplementedError("reset_noise_scale != 0 is not built")
         self.render_mode = render_mode
         self.md = M.load_model(xml_file)
         self._model, self._keep = M.model_struct(self.md)
@@ -83,7 +78,10 @@ class _SingleEnv:
         self.h = h
         lo, hi = self.md["ctrlrange"]
         self.action_space = Box(np.full(6, lo, np.float32), np.full(6, hi, np.float32), dtype=np.float32)
-        self.observation_space = Box(-np.inf, np.inf, shape=(self.obs_dim,), dtype=np.float64)
+        # use_contact_forces: the reference DECLARES 84 more observation slots (tr_env.py:263-264) but its _get_obs never
+        # fills them (:529-646), so the vectors it returns keep obs_dim entries; the declared space follows the reference
+        declared = self.obs_dim + (84 if self.cfg.use_contact_forces else 0)
+        self.observation_space = Box(-np.inf, np.inf, shape=(declared,), dtype=np.float64)
         self.init_qpos = np.array(self.md["qpos0"])
         self.init_qvel = np.zeros(18)
         self.model = self.md

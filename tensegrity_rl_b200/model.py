@@ -68,6 +68,8 @@ class TsgEnvConfig(C.Structure):
         ("ditch_reward_max", d), ("ditch_reward_stdev", d), ("waypt_reward_amplitude", d), ("waypt_reward_stdev", d),
         ("kill_force", d), ("reset_pose", (d * NQ) * NPOSE),
         ("use_obs_noise", i32), ("pad_noise_", i32), ("obs_noise_tendon_stdev", d), ("obs_noise_cap_pos_stdev", d),
+        ("reset_noise_scale", d), ("use_contact_forces", i32), ("pad_contact_", i32), ("contact_cost_weight", d),
+        ("contact_force_range", d * 2),
     ]
 
 
@@ -377,7 +379,8 @@ def env_config(md, env_kind="tr_env", desired_action="straight", desired_directi
                way_pts_range=(2.5, 3.5), way_pts_angle_range=(-math.pi / 6, math.pi / 6),
                ditch_reward_max=300, ditch_reward_stdev=0.15, waypt_reward_amplitude=100, waypt_reward_stdev=0.10,
                yaw_reward_weight=1, max_episode_steps=5000, frame_skip=20, warmup_steps=50,
-               use_obs_noise=False, obs_noise_tendon_stdev=0.02, obs_noise_cap_pos_stdev=0.05):
+               use_obs_noise=False, obs_noise_tendon_stdev=0.02, obs_noise_cap_pos_stdev=0.05,
+               reset_noise_scale=0.0, use_contact_forces=False, contact_cost_weight=5e-4, contact_force_range=None):
     """Defaults per env: tr_env.py:137-173 / tensegrity_env.py:160-181."""
     legacy = env_kind in ("tensegrity_env", ENV_LEGACY)
     c = TsgEnvConfig()
@@ -420,6 +423,12 @@ def env_config(md, env_kind="tr_env", desired_action="straight", desired_directi
         raise ValueError("use_obs_noise is a tr_env option (tr_env.py:142)")
     c.use_obs_noise = int(bool(use_obs_noise))          # tr_env.py:142,236
     c.obs_noise_tendon_stdev, c.obs_noise_cap_pos_stdev = obs_noise_tendon_stdev, obs_noise_cap_pos_stdev   # :161-162
+    c.reset_noise_scale = float(reset_noise_scale)       # tr_env.py:152,734-743
+    c.use_contact_forces = int(bool(use_contact_forces))  # tr_env.py:140,513-516
+    c.contact_cost_weight = contact_cost_weight
+    if contact_force_range is None:                       # tr_env.py:149-151,255-256
+        contact_force_range = (-1000.0, 1000.0) if (desired_action == "turn" and not legacy) else (-1.0, 1.0)
+    _fill(c.contact_force_range, contact_force_range)
     poses = np.zeros((NPOSE, NQ))
     if legacy:
         c.npose = 1

@@ -148,6 +148,13 @@ class Emul:
         return o[0], i[0]
 
 
+def reset_noise(seed, stream, nreset):
+    """the 21 uniform(-1, 1) qpos offsets and 18 standard-normal qvel values of reset `nreset` of stream `stream`"""
+    out = np.zeros(39)
+    lib().tbe_reset_noise(C.c_ulonglong(seed), C.c_ulonglong(stream), C.c_ulonglong(nreset), P(out))
+    return out[:21], out[21:]
+
+
 def obs_normals(seed, stream, nreset, step, n, reverse=False):
     """the standard-normal draws the CUDA source uses for the observation of (stream, reset count, episode step)"""
     out = np.zeros(n + 1)

@@ -232,6 +232,9 @@ void tbe_mj_step_f32(void* h, int n, double* rec, const double* ctrl, int nstep,
     store_env(S, L, on, A, r);
   });
 }
+void tbe_reset_noise(unsigned long long seed, unsigned long long stream, unsigned long long nreset, double* out39) {
+  for (int i = 0; i < NQ + NV; i++) out39[i] = reset_noise_draw(seed, stream, nreset, i);
+}
 void tbe_make_draws(double* d, unsigned long long seed, unsigned long long env_id, unsigned long long nreset) {
   make_draws(d, seed, env_id, nreset);
 }

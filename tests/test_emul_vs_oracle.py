@@ -218,3 +218,30 @@ def test_obs_noise_draws_are_standard_normal_and_keyed():
 def test_obs_noise_is_a_tr_env_option():
     with pytest.raises(ValueError):
         E.Emul("flat", env_kind="tensegrity_env", use_obs_noise=True)
+
+
+def test_reset_noise_and_contact_cost_parity():
+    """reset_noise_scale (tr_env.py:734-743: qpos += U(-s, s), qvel = s N(0, 1), Philox-keyed here) and
+    use_contact_forces (:292-304, 513-516: reward -= w sum(clip(cfrc_ext)^2), info["reward_ctrl"] = -contact_cost)
+    against the oracle env fed the same draws."""
+    rng = np.random.default_rng(21)
+    kw = dict(desired_action="tracking", reset_noise_scale=0.02, use_contact_forces=True, contact_cost_weight=5e-4,
+              contact_force_range=(-50.0, 50.0))
+    oe = OracleEnv("flat", "tr_env", **kw)
+    em = E.Emul("flat", env_kind="tr_env", **kw)
+    draws = np.concatenate([rng.uniform(0, 1, 2), rng.standard_normal(6), rng.uniform(0, 1, 2)])
+    nz = E.reset_noise(41, 6, 0)
+    assert np.abs(nz[0]).max() <= 1 and nz[0].std() > 0.3 and abs(nz[1].mean()) < 0.8
+    o1, o2 = oe.reset(draws, noise=nz), em.reset(draws, seed=41, env_id=6)
+    assert np.abs(o1 - o2).max() < 1e-7
+    # the noise moved the reset: the same draws without it give another observation
+    assert np.abs(OracleEnv("flat", "tr_env", desired_action="tracking").reset(draws) - o1).max() > 1e-3
+    costs = []
+    for st in range(10):
+        a = rng.uniform(-0.45, 0.15, 6)
+        ob1, r1, t1, tr1, i1 = oe.step(a)
+        ob2, r2, d2, info = em.step(a)
+        assert np.abs(ob1 - ob2).max() < 1e-7 and abs(r1 - r2) <= 1e-7 * max(1.0, abs(r1))
+        assert info[1] == pytest.approx(i1["reward_ctrl"], rel=1e-7, abs=1e-9)
+        costs.append(-i1["reward_ctrl"])
+    assert max(costs) > 0.1      # the contact cost is really in play (wrenches of order 100 N clipped at 50)
