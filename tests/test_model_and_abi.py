@@ -3,6 +3,7 @@ import ctypes as C
 import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -148,3 +149,35 @@ def test_policy_assets_and_actor_cpu():
     mu = x @ torch.tensor(a["Wmu"]).t() + torch.tensor(a["bmu"])
     ref = -0.45 + 0.5 * (torch.tanh(mu) + 1) * 0.6
     assert torch.allclose(d, ref, atol=1e-5)
+
+
+def test_run_py_shims(monkeypatch):
+    """shims/: the module names run.py imports (`mujoco`, `tr_env`, run.py:4,8,158), so that it runs unmodified with
+    shims/ on PYTHONPATH.  gym is not installed here: a stub `gym.envs.registration` records the registrations."""
+    import importlib
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "shims"))
+    calls = []
+    gym = types.ModuleType("gym"); envs = types.ModuleType("gym.envs"); reg = types.ModuleType("gym.envs.registration")
+    reg.register = lambda **kw: calls.append(kw)
+    gym.envs, envs.registration = envs, reg
+    for name, mod in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    for name in ("mujoco", "tr_env", "tr_env.envs", "tensegrity_env", "tensegrity_env.envs"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    mujoco = importlib.import_module("mujoco")
+    tr = importlib.import_module("tr_env")
+    te = importlib.import_module("tensegrity_env")
+    assert {c["id"] for c in calls} == {"tr_env-v0", "tensegrity_env-v0"}
+    assert all(c["max_episode_steps"] == 5000 for c in calls)
+    assert [c["entry_point"] for c in calls if c["id"] == "tr_env-v0"] == ["tr_env.envs:tr_env"]
+    from tensegrity_rl_b200 import envs as E
+    assert importlib.import_module("tr_env.envs").tr_env is E.tr_env
+    assert importlib.import_module("tensegrity_env.envs").tensegrity_env is E.tensegrity_env
+    # mj_contactForce on the contact shim: the aggregated bar-bar force lands in forcetorque[0] (run.py:155-161)
+    data = types.SimpleNamespace(contact=[E._Contact(1, 6, 12.5)])
+    ft = np.zeros(6)
+    mujoco.mj_contactForce(None, data, 0, ft)
+    assert ft[0] == 12.5 and np.all(ft[1:] == 0)
+    assert data.contact[0].geom1 != 0 and data.contact[0].geom2 != 0
