@@ -343,9 +343,16 @@ class SACLearner:
 
     def save(self, path):
         """SB3 zip layout: policy.pth / pytorch_variables.pth / *.optimizer.pth / data / _stable_baselines3_version.
-        `data` is the source checkpoint's (when resumed from one: stays loadable by SB3) with the counters updated,
-        else a plain-JSON record of the hyper-parameters and spaces."""
+        A learner resumed from an SB3 checkpoint (load_sb3_zip) re-uses that checkpoint's `data` entry with the counters
+        updated, so `SAC.load` reads the result.  A learner started from scratch has no serialized SB3 `Space` /
+        `policy_class` objects to put there: its `data` is a plain-JSON record of hyper-parameters and shapes, which
+        `SacActor` and `load_sb3_zip` read but `SAC.load` rejects (only policy.pth and the optimizer files are
+        SB3-compatible); a warning says so."""
         torch = self.torch
+        if not self._source_data:
+            import warnings
+            warnings.warn("SACLearner.save: not resumed from an SB3 checkpoint -- the zip's `data` entry is plain JSON; "
+                          "stable_baselines3.SAC.load cannot read it (policy.pth / optimizer files are compatible)")
         def dump(obj):
             b = io.BytesIO()
             torch.save(obj, b)
