@@ -221,9 +221,17 @@ template <typename real, typename MR> TB_FN real con_update(Con<real>& c, const 
   return cost;
 }
 // cost and its first two derivatives along the search direction at step a, for one contact
-template <typename real, typename MR> TB_FN void con_ls(const Con<real>& k, const ModelT<MR>& m, real a, real& cost, real& d0, real& d1) {
+// (coefficients: U0, V0, UU, UV, VV, q0, q1, q2, D0 -- of a contact in memory, or cached in registers by the caller)
+template <typename real> struct LsCoef { real U0, V0, UU, UV, VV, q0, q1, q2, D0; };
+template <typename real> TB_FN LsCoef<real> ls_coef(const Con<real>& k) {
+  LsCoef<real> c;
+  c.U0 = k.t.ls.U0; c.V0 = k.t.ls.V0; c.UU = k.t.ls.UU; c.UV = k.t.ls.UV; c.VV = k.t.ls.VV;
+  c.q0 = k.t.ls.q0; c.q1 = k.t.ls.q1; c.q2 = k.t.ls.q2; c.D0 = k.D0;
+  return c;
+}
+template <typename real, typename MR> TB_FN void con_ls(const LsCoef<real>& k, const ModelT<MR>& m, real a, real& cost, real& d0, real& d1) {
   real mu = (real)m.mu;
-  const real U0 = k.t.ls.U0, V0 = k.t.ls.V0, UU = k.t.ls.UU, UV = k.t.ls.UV, VV = k.t.ls.VV;
+  const real U0 = k.U0, V0 = k.V0, UU = k.UU, UV = k.UV, VV = k.VV;
   real N = U0 + a * V0, Tsqr = UU + a * (2 * UV + a * VV);
   bool bottom = false;
   if (Tsqr <= 0) { if (N < 0) bottom = true; }
@@ -241,7 +249,7 @@ template <typename real, typename MR> TB_FN void con_ls(const Con<real>& k, cons
       d1 += Dm * ((N1 - mu * T1) * (N1 - mu * T1) + NT * (-mu * T2));
     }
   }
-  if (bottom) { cost += a * a * k.t.ls.q2 + a * k.t.ls.q1 + k.t.ls.q0; d0 += 2 * a * k.t.ls.q2 + k.t.ls.q1; d1 += 2 * k.t.ls.q2; }
+  if (bottom) { cost += a * a * k.q2 + a * k.q1 + k.q0; d0 += 2 * a * k.q2 + k.q1; d1 += 2 * k.q2; }
 }
 
 // ---- Hessian of one contact in world-frame coordinates (per bar: linear dofs, world angular dofs).
@@ -1121,6 +1129,8 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
     }
     sreal alpha = 0;
     int evals = 1;
+    LsCoef<sreal> lc0 = LsCoef<sreal>();   // the lane's first contact stays in registers for the evaluations
+    if (go && nmine > 0) lc0 = ls_coef(con_of(S, b, 0));
     {
       struct Pnt { sreal alpha, cost, d0, d1; };
       // W_*: waiting for the evaluation it requested; L_*: pure logic, resolved without an evaluation
@@ -1135,13 +1145,13 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       sreal aeval = 0;
       auto newton = [&](const Pnt& p) { return p.alpha - tdiv(p.d0, p.d1); };
       // update_bracket against the candidates captured at the mid-point evaluation: (old p1next = c0, p2next, pmid)
+      auto bracket1 = [&](Pnt& p, const Pnt& q, int& flag) {
+        if (p.d0 < 0 && q.d0 < 0 && p.d0 < q.d0) { p = q; flag = 1; }
+        else if (p.d0 > 0 && q.d0 > 0 && p.d0 > q.d0) { p = q; flag = 2; }
+      };
       auto bracket = [&](Pnt& p) {
         int flag = 0;
-        const Pnt* cand[3] = {&c0, &p2next, &pmid};
-        for (int i = 0; i < 3; i++) {
-          if (p.d0 < 0 && cand[i]->d0 < 0 && p.d0 < cand[i]->d0) { p = *cand[i]; flag = 1; }
-          else if (p.d0 > 0 && cand[i]->d0 > 0 && p.d0 > cand[i]->d0) { p = *cand[i]; flag = 2; }
-        }
+        bracket1(p, c0, flag); bracket1(p, p2next, flag); bracket1(p, pmid, flag);
         return flag;
       };
       if (go && !(snorm < SMINV)) { st = W_P1; aeval = newton(p0); }
@@ -1152,8 +1162,9 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
         sreal c_ = 0, d0_ = 0, d1_ = 0;
         if (ev) {
           if (nmine > 0) {
+            con_ls(lc0, m, aeval, c_, d0_, d1_);
             TB_UNROLL1
-            for (int s = 0; s < nmine; s++) con_ls(con_of(S, b, s), m, aeval, c_, d0_, d1_);
+            for (int s = 1; s < nmine; s++) con_ls(ls_coef(con_of(S, b, s)), m, aeval, c_, d0_, d1_);
           }
           c_ += aeval * aeval * qG2 + aeval * qG1 + gauss; d0_ += 2 * aeval * qG2 + qG1; d1_ += 2 * qG2;
         }
@@ -1177,11 +1188,11 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
             case W_MID: {
               pmid = r;
               c0 = p1next;
-              const Pnt* cand[3] = {&c0, &p2next, &pmid};
-              int best = -1; sreal bestcost = 0;
-              for (int i = 0; i < 3; i++)
-                if (tabs(cand[i]->d0) < gtol && (best == -1 || cand[i]->cost < bestcost)) { bestcost = cand[i]->cost; best = i; }
-              if (best >= 0) { alpha = cand[best]->alpha; st = LS_DONE; }
+              int best = -1; sreal bestcost = 0, bestalpha = 0;
+              if (tabs(c0.d0) < gtol) { bestcost = c0.cost; bestalpha = c0.alpha; best = 0; }
+              if (tabs(p2next.d0) < gtol && (best == -1 || p2next.cost < bestcost)) { bestcost = p2next.cost; bestalpha = p2next.alpha; best = 1; }
+              if (tabs(pmid.d0) < gtol && (best == -1 || pmid.cost < bestcost)) { bestcost = pmid.cost; bestalpha = pmid.alpha; best = 2; }
+              if (best >= 0) { alpha = bestalpha; st = LS_DONE; }
               else {
                 b1 = bracket(p1) != 0;
                 if (b1) { aeval = newton(p1); st = W_B1; } else st = L_DOB2;

@@ -36,17 +36,17 @@ template <typename real> TB_FN void obj_support(const CObj<real>& o, const real*
     out[0] = o.px[best % 3]; out[1] = o.py[best % 3]; out[2] = best < 3 ? o.pbase : o.pz[best - 3];
     return;
   }
-  real ld[3], res[3];
-  mulMTV(ld, o.R, dir);
-  if (o.type == GEOM_SPHERE) scl3(res, ld, o.size[0]);
-  else {
-    real tmp = tsqrt(ld[0] * ld[0] + ld[1] * ld[1]);
-    if (tmp > Lim<real>::MINVAL) { real it = o.size[0] / tmp; res[0] = ld[0] * it; res[1] = ld[1] * it; }
-    else res[0] = res[1] = 0;
-    res[2] = (ld[2] > 0 ? real(1) : (ld[2] < 0 ? real(-1) : real(0))) * o.size[1];
-  }
-  mulMV(out, o.R, res);
-  add3(out, out, o.pos);
+  // spheres and cylinders are bodies of revolution about the bar axis a (third column of R): the support point is
+  // pos + r perp / |perp| + sign(dir . a) h a with perp = dir - (dir . a) a  (sphere: pos + r dir) -- the same point as
+  // R * support_local(R^T dir), without the two rotations
+  if (o.type == GEOM_SPHERE) { for (int k = 0; k < 3; k++) out[k] = o.pos[k] + o.size[0] * dir[k]; return; }
+  const real a[3] = {o.R[2], o.R[5], o.R[8]};
+  const real da = dot3(dir, a);
+  real perp[3] = {dir[0] - da * a[0], dir[1] - da * a[1], dir[2] - da * a[2]};
+  const real tmp = tsqrt(dot3(perp, perp));
+  const real s = tmp > Lim<real>::MINVAL ? tdiv(o.size[0], tmp) : real(0);
+  const real hz = (da > 0 ? real(1) : (da < 0 ? real(-1) : real(0))) * o.size[1];
+  for (int k = 0; k < 3; k++) out[k] = o.pos[k] + s * perp[k] + hz * a[k];
 }
 template <typename real> TB_FN void obj_center(const CObj<real>& o, real* c) {
   if (o.type == 100) {
