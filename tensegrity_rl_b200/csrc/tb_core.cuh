@@ -139,19 +139,19 @@ template <typename real> TB_FN void make_frame(real* f) {
 }
 // out = J x, x given as world-frame twists per bar (lin, world angular) in xv
 template <typename real, typename V> TB_FN void con_mulJ(const Con<real>& c, const V* xvv, real* out) {
-  real xv[NV];
-  for (int k = 0; k < 6; k++) { xv[6 * c.b2 + k] = (real)xvv[6 * c.b2 + k]; if (c.b1 >= 0) xv[6 * c.b1 + k] = (real)xvv[6 * c.b1 + k]; }
-  real rel[3], relw[3], t[3];
-  const real* w2 = xv + 6 * c.b2 + 3;
-  cross3(t, w2, c.r2);
-  add3(rel, xv + 6 * c.b2, t);
-  copy3(relw, w2);
+  real v2[6], rel[3], relw[3], t[3];   // statically indexed copies only: a dynamically indexed array would live in local memory
+  const V* p2 = xvv + 6 * c.b2;
+  for (int k = 0; k < 6; k++) v2[k] = (real)p2[k];
+  cross3(t, v2 + 3, c.r2);
+  add3(rel, v2, t);
+  copy3(relw, v2 + 3);
   if (c.b1 >= 0) {
-    const real* w1 = xv + 6 * c.b1 + 3;
-    real u1[3];
-    cross3(t, w1, c.r1);
-    add3(u1, xv + 6 * c.b1, t);
-    sub3(rel, rel, u1); sub3(relw, relw, w1);
+    real v1[6], u1[3];
+    const V* p1 = xvv + 6 * c.b1;
+    for (int k = 0; k < 6; k++) v1[k] = (real)p1[k];
+    cross3(t, v1 + 3, c.r1);
+    add3(u1, v1, t);
+    sub3(rel, rel, u1); sub3(relw, relw, v1 + 3);
   }
   for (int a = 0; a < 3; a++) { out[a] = dot3(c.frame + 3 * a, rel); out[3 + a] = dot3(c.frame + 3 * a, relw); }
 }
@@ -792,7 +792,7 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
           o1.pbase = pr.pbase;
           o2.type = m.gtype[Gi]; o2.size[0] = r; o2.size[1] = hl;
           for (int k = 0; k < 3; k++) o2.pos[k] = pos[k];
-          for (int k = 0; k < 9; k++) o2.R[k] = R[k];
+          for (int k = 0; k < 3; k++) o2.axis[k] = R[3 * k + 2];
           nmpr++;
         }
         sreal depthS = 0, dirS[3] = {0, 0, 1}, cpS[3] = {0, 0, 0};
@@ -877,7 +877,7 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
         }
         o1.type = m.gtype[g1]; o1.size[0] = m.gsize[g1][0]; o1.size[1] = m.gsize[g1][1];
         o2.type = m.gtype[g2]; o2.size[0] = m.gsize[g2][0]; o2.size[1] = m.gsize[g2][1];
-        for (int k = 0; k < 9; k++) { o1.R[k] = Ra[k]; o2.R[k] = Rb[k]; }
+        for (int k = 0; k < 3; k++) { o1.axis[k] = Ra[3 * k + 2]; o2.axis[k] = Rb[3 * k + 2]; }
         for (int k = 0; k < 3; k++) { o1.pos[k] = Xa[k] + Ra[3 * k + 2] * m.gz[g1]; o2.pos[k] = Xb[k] + Rb[3 * k + 2] * m.gz[g2]; }
         nmpr++;
       }

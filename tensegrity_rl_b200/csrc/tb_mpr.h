@@ -7,11 +7,11 @@
 
 namespace tb {
 
-// type GEOM_SPHERE / GEOM_CYL: centre pos, rotation R (row-major, body frame -> world), size = (radius, half length).
+// type GEOM_SPHERE / GEOM_CYL: centre pos, unit axis (the bar axis in the world frame), size = (radius, half length).
 // type 100 = height-field prism: its three (x, y) columns with the top heights and the common base height; vertex
 // i < 3 is (px[i], py[i], pbase), vertex 3 + i is (px[i], py[i], pz[i]).
 template <typename real>
-struct CObj { int type; real pos[3]; real R[9]; real size[2]; real px[3], py[3], pz[3], pbase; };
+struct CObj { int type; real pos[3]; real axis[3]; real size[2]; real px[3], py[3], pz[3], pbase; };
 template <typename real> struct Supp { real v[3], v1[3]; };  // v = v1 - v2 ; v2 recovered as v1 - v
 
 template <typename real> TB_FN bool ccd_is_zero(real x) { return tabs(x) < Lim<real>::EPS; }
@@ -26,21 +26,25 @@ template <typename real> TB_FN void ccd_normalize(real* v) { real s = trcp(tsqrt
 
 template <typename real> TB_FN void obj_support(const CObj<real>& o, const real* dir, real* out) {
   if (o.type == 100) {
-    // first maximum of vertex . dir over the vertices in order (bottom 0..2, top 3..5), as libccd's loop finds it
-    real t[3], bd = 0; int best = 0;
+    // first maximum of vertex . dir over the vertices in order (bottom 0..2, top 3..5), as libccd's loop finds it; the
+    // winner's coordinates are carried along (no dynamic index: the object stays in registers)
+    real t[3], bd = 0, bx = 0, by = 0, bz = 0;
+    TB_UNROLL
     for (int j = 0; j < 3; j++) t[j] = o.px[j] * dir[0] + o.py[j] * dir[1];
+    TB_UNROLL
     for (int i = 0; i < 6; i++) {
-      real dd = t[i % 3] + (i < 3 ? o.pbase : o.pz[i - 3]) * dir[2];
-      if (i == 0 || dd > bd) { bd = dd; best = i; }
+      const real vz = i < 3 ? o.pbase : o.pz[i % 3];
+      const real dd = t[i % 3] + vz * dir[2];
+      if (i == 0 || dd > bd) { bd = dd; bx = o.px[i % 3]; by = o.py[i % 3]; bz = vz; }
     }
-    out[0] = o.px[best % 3]; out[1] = o.py[best % 3]; out[2] = best < 3 ? o.pbase : o.pz[best - 3];
+    out[0] = bx; out[1] = by; out[2] = bz;
     return;
   }
   // spheres and cylinders are bodies of revolution about the bar axis a (third column of R): the support point is
   // pos + r perp / |perp| + sign(dir . a) h a with perp = dir - (dir . a) a  (sphere: pos + r dir) -- the same point as
   // R * support_local(R^T dir), without the two rotations
   if (o.type == GEOM_SPHERE) { for (int k = 0; k < 3; k++) out[k] = o.pos[k] + o.size[0] * dir[k]; return; }
-  const real a[3] = {o.R[2], o.R[5], o.R[8]};
+  const real a[3] = {o.axis[0], o.axis[1], o.axis[2]};
   const real da = dot3(dir, a);
   real perp[3] = {dir[0] - da * a[0], dir[1] - da * a[1], dir[2] - da * a[2]};
   const real tmp = tsqrt(dot3(perp, perp));
@@ -51,7 +55,8 @@ template <typename real> TB_FN void obj_support(const CObj<real>& o, const real*
 template <typename real> TB_FN void obj_center(const CObj<real>& o, real* c) {
   if (o.type == 100) {
     c[0] = c[1] = c[2] = 0;
-    for (int i = 0; i < 6; i++) { c[0] += o.px[i % 3]; c[1] += o.py[i % 3]; c[2] += i < 3 ? o.pbase : o.pz[i - 3]; }
+    TB_UNROLL
+    for (int i = 0; i < 6; i++) { c[0] += o.px[i % 3]; c[1] += o.py[i % 3]; c[2] += i < 3 ? o.pbase : o.pz[i % 3]; }
     c[0] /= 6; c[1] /= 6; c[2] /= 6;
   } else copy3(c, o.pos);
 }
