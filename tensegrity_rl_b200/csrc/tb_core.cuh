@@ -780,8 +780,11 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       TB_UNROLL1
       while (any(cand != 0)) {
         const bool has = cand != 0;
-        CObj<sreal> o1, o2;   // the narrow phase runs in the solver's precision: MPR's 1e-6 tolerance is out of fp32's reach
-        o1 = CObj<sreal>(); o2 = o1;
+        // the narrow phase runs in the solver's precision: MPR's 1e-6 tolerance is out of fp32's reach.  The lane's two
+        // objects live in the env's solver scratch (unused until the Newton stage), not in per-thread local memory; only
+        // lanes with a candidate write them (the idle lanes 30, 31 alias the last env's slice)
+        CObj<sreal>* objs = reinterpret_cast<CObj<sreal>*>(&S.u.sol.D[0][0]) + 2 * b;
+        CObj<sreal>&o1 = objs[0], &o2 = objs[1];
         if (has) {
           const int q = lowbit(cand);
           cand &= cand - 1;
@@ -864,8 +867,8 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
     while (any(cand != 0)) {
       const bool has = cand != 0;
       int cb1 = pb1, cb2 = pb2;
-      CObj<sreal> o1, o2;
-      o1 = CObj<sreal>(); o2 = o1;
+      CObj<sreal>* objs = reinterpret_cast<CObj<sreal>*>(&S.u.sol.D[0][0]) + 2 * b;
+      CObj<sreal>&o1 = objs[0], &o2 = objs[1];
       if (has) {
         const int i = lowbit(cand);
         cand &= cand - 1;

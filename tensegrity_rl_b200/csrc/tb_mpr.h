@@ -123,10 +123,9 @@ template <typename real> TB_FN real tri_dist2_origin(const real* x0, const real*
 // instruction stream, and the portal lives in registers.  Warp-collective (every lane of the warp calls it).
 // Returns true on penetration; dir points from obj1 to obj2.
 template <typename real>
-TB_NOINL bool mpr_penetration(const CObj<real>& o1g, const CObj<real>& o2g, real tol, int max_iter, bool has,
+TB_NOINL bool mpr_penetration(const CObj<real>& o1, const CObj<real>& o2, real tol, int max_iter, bool has,
                               real* depth, real* dir_out, real* pos_out) {
   enum { S1 = 0, S2, S3, S4, S5, DONE };
-  const CObj<real> o1 = o1g, o2 = o2g;
   Supp<real> p0, p1, p2, p3, v4;
   real dir[3] = {1, 0, 0}, c2[3] = {0, 0, 0};
   int st = DONE, it = 0;
