@@ -20,7 +20,7 @@ for l in open(dis):
         cnt[cur] += 1; lines[(cur, loc)] += 1; grp = False
 print("device functions:", cnt.most_common(), "total", sum(cnt.values()))
 agg = collections.Counter()
-for fname in ("tsg_core.cuh", "tsg_env.cuh"):
+for fname in ("tb_core.cuh", "tb_env.cuh", "tb_mpr.h"):
     src = open(root + "/tensegrity_rl_b200/csrc/" + fname).read().split('\n')
     fl = [(i + 1, re.search(r'(\w+)\(', l.split('TSG_FN', 1)[1].replace('_NOINLINE', '')).group(1)) for i, l in enumerate(src) if l.startswith('TSG_FN')]
     starts = [x[0] for x in fl]
@@ -29,5 +29,5 @@ for fname in ("tsg_core.cuh", "tsg_env.cuh"):
             k = bisect.bisect_right(starts, lc[1]) - 1
             agg[(f[-12:], fl[k][1] if k >= 0 else '?')] += n
 for (f, lc), n in lines.items():
-    if not lc or lc[0] not in ("tsg_core.cuh", "tsg_env.cuh"): agg[(f[-12:], str(lc[0]) if lc else None)] += n
+    if not lc or lc[0] not in ("tb_core.cuh", "tb_env.cuh", "tb_mpr.h"): agg[(f[-12:], str(lc[0]) if lc else None)] += n
 for k, v in agg.most_common(40): print(v, k)
