@@ -270,8 +270,8 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * ksteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": n * 6 * 8,
-               "d2h_bytes_per_step": n * (env.obs_dim * 8 + 8 + 1), "steps": ksteps,
+        e2e = {"value": world * n * ksteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": world * n * 6 * 8,
+               "d2h_bytes_per_step": world * n * (env.obs_dim * 8 + 8 + 1), "steps": ksteps,
                "warmup": kwarm,
                "api": "TensegrityVecEnv.step_tensor with pinned host ctrl/obs/reward/done copies, wall clock, no L2 flush"}
 

@@ -89,12 +89,13 @@ struct EnvSh {
 };
 
 struct LaneCtx { int lane, grp, bar, base; bool valid; };
-TB_FN LaneCtx make_lane() {
+// epw <= EPW: envs this warp works on (its remaining lanes idle along, aliasing the last env's slice read-only)
+TB_FN LaneCtx make_lane(int epw = EPW) {
   LaneCtx L;
   L.lane = simt_lane();
-  L.valid = L.lane < G * EPW;
-  L.grp = L.valid ? L.lane / G : EPW - 1;
-  L.bar = L.valid ? L.lane % G : L.lane - G * EPW;
+  L.valid = L.lane < G * epw;
+  L.grp = L.valid ? L.lane / G : epw - 1;
+  L.bar = L.lane % G;
   L.base = L.grp * G;
   return L;
 }

@@ -24,6 +24,9 @@ using namespace tb;
 #ifndef TB_WARPS_SMALL
 #define TB_WARPS_SMALL 2   // second CTA shape of the step kernel (two CTAs per SM), for batches that fit the machine at once
 #endif
+#ifndef TB_EPW_SMALL
+#define TB_EPW_SMALL 10    // envs per warp in that shape (fewer envs per warp = fewer envs waiting for the slowest one)
+#endif
 #ifndef TB_ALIGN
 #define TB_ALIGN 1
 #endif
@@ -39,14 +42,14 @@ template <typename P> __host__ __device__ constexpr size_t smem_model() { return
 constexpr size_t SMEM_CFG = align16(sizeof(EnvCfg));
 // env slices are spaced by an odd number of 16-byte units, so that the same field of the ten envs of a warp falls into different banks
 template <typename P> __host__ __device__ constexpr size_t envsh_stride() { return align16(sizeof(EnvSh<P>)) | 16; }
-template <typename P, int W> constexpr size_t smem_bytes() { return smem_model<P>() + SMEM_CFG + (size_t)W * EPW * envsh_stride<P>(); }
+template <typename P, int W, int E = EPW> constexpr size_t smem_bytes() { return smem_model<P>() + SMEM_CFG + (size_t)W * E * envsh_stride<P>(); }
 
 // Persistent CTAs: the grid fills the machine once (SMs x resident CTAs) and every CTA pulls rounds of TB_WARPS chunks
 // (a chunk = EPW consecutive envs, or pool slots, stepped by one warp) from a global counter until the batch is done,
 // so rounds of different cost (contact count, Newton iterations, resets) balance dynamically.  The env rounds come
 // first, then the pool rounds, so that all warps of a CTA always run the same program.  The model constants are
 // staged once per CTA in shared memory.
-template <typename P, int MODE, int W>
+template <typename P, int MODE, int W, int E = EPW>
 __global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const ModelT<typename P::real>* __restrict__ gm,
                                                                             const EnvCfg* __restrict__ gc, StepIO io,
                                                                             Con<typename P::sreal>* __restrict__ spill_base) {
@@ -64,14 +67,14 @@ __global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const Model
   __syncthreads();
   const ModelT<real>& m = *reinterpret_cast<const ModelT<real>*>(tb_smem);
   const EnvCfg& c = *reinterpret_cast<const EnvCfg*>(tb_smem + smem_model<P>());
-  const LaneCtx L = make_lane();
+  const LaneCtx L = make_lane(E);
   const int warp = threadIdx.x >> 5;
   EnvSh<P>& S = *reinterpret_cast<EnvSh<P>*>(tb_smem + smem_model<P>() + SMEM_CFG +
-                                                   (size_t)(warp * EPW + L.grp) * envsh_stride<P>());
+                                                   (size_t)(warp * E + L.grp) * envsh_stride<P>());
   if (L.valid && L.bar == 0) S.spill = spill_base + (size_t)((blockIdx.x * W + warp) * EPW + L.grp) * (3 * KS);
   __syncwarp();
-  const int env_chunks = (io.n_envs + EPW - 1) / EPW, env_rounds = (env_chunks + W - 1) / W;
-  const int pool_chunks = (MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? (io.n_pool + EPW - 1) / EPW : 0;
+  const int env_chunks = (io.n_envs + E - 1) / E, env_rounds = (env_chunks + W - 1) / W;
+  const int pool_chunks = (MODE == MODE_STEP || (MODE == MODE_RESET && !io.mask)) ? (io.n_pool + E - 1) / E : 0;
   const int pool_rounds = (pool_chunks + W - 1) / W;
   for (;;) {
     __syncthreads();
@@ -80,11 +83,11 @@ __global__ void __launch_bounds__(W * 32, TB_MIN_CTAS) tb_env_kernel(const Model
     const int round = s_round;
     if (round >= env_rounds + pool_rounds) break;
     if (round < env_rounds) {
-      const int first = (round * W + warp) * EPW;   // may lie beyond the batch: the warp then idles in step
+      const int first = (round * W + warp) * E;   // may lie beyond the batch: the warp then idles in step
       if (MODE == MODE_STEP) run_step(S, m, c, io, L, first, TB_ALIGN != 0);
       else if (MODE == MODE_RESET) run_reset(S, m, c, io, L, first);
       else run_forward(S, m, c, io, L, first);
-    } else run_pool(S, m, c, io, L, ((round - env_rounds) * W + warp) * EPW, MODE == MODE_RESET);
+    } else run_pool(S, m, c, io, L, ((round - env_rounds) * W + warp) * E, MODE == MODE_RESET);
   }
 }
 
@@ -190,7 +193,7 @@ struct TsgHandle {
   double* d_pool_obs; double* d_pool_real_obs; int* d_lists; int* d_counts; uint8_t* d_need_sync;
   double* real_obs;   // where the noise-free observation goes with use_obs_noise: d_realobs_own or the caller's buffer
   double* d_realobs_own;
-  int grid[3], grid_small, shape, regs;   // shape: 0 = TB_WARPS, 1 = TB_WARPS_SMALL warps per CTA in the step kernel
+  int grid[3], grid_small, shape, regs, warps, epw;   // shape: 0 = TB_WARPS, 1 = TB_WARPS_SMALL warps per CTA in the step kernel
   size_t smem;
   cudaStream_t own_stream;
 };
@@ -216,10 +219,10 @@ static size_t extra_smem() {
   if (v < 0) { const char* e = getenv("TSG_EXTRA_SMEM"); v = e ? atol(e) : 0; }
   return (size_t)v;
 }
-template <typename P, int MODE, int W>
+template <typename P, int MODE, int W, int E = EPW>
 static int launch_w(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot, int grid) {
   io.counter = h->d_counter + counter_slot;
-  tb_env_kernel<P, MODE, W><<<grid, W * 32, smem_bytes<P, W>() + extra_smem(), s>>>(
+  tb_env_kernel<P, MODE, W, E><<<grid, W * 32, smem_bytes<P, W, E>() + extra_smem(), s>>>(
       (const ModelT<typename P::real>*)h->d_model, h->d_cfg, io, (Con<typename P::sreal>*)h->d_spill);
   CK(cudaGetLastError());
   h->launches++;
@@ -227,7 +230,7 @@ static int launch_w(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot, 
 }
 template <typename P, int MODE>
 static int launch_t(TsgHandle* h, StepIO& io, cudaStream_t s, int counter_slot) {
-  if (MODE == MODE_STEP && h->shape == 1) return launch_w<P, MODE_STEP, TB_WARPS_SMALL>(h, io, s, counter_slot, h->grid_small);
+  if (MODE == MODE_STEP && h->shape == 1) return launch_w<P, MODE_STEP, TB_WARPS_SMALL, TB_EPW_SMALL>(h, io, s, counter_slot, h->grid_small);
   return launch_w<P, MODE, TB_WARPS>(h, io, s, counter_slot, h->grid[MODE]);
 }
 // counter_slot: which of the handle's work counters the launch consumes (they are zeroed together, once per API call)
@@ -239,33 +242,36 @@ static int zero_counters(TsgHandle* h, cudaStream_t s) {
   CK(cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(int), s));
   return 0;
 }
-template <typename P, int MODE, int W>
-static int setup_kernel(TsgHandle* h, int num_sms, int* grid) {
-  size_t smem = smem_bytes<P, W>() + extra_smem();
-  CK(cudaFuncSetAttribute(tb_env_kernel<P, MODE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <typename P, int MODE, int W, int E = EPW>
+static int setup_kernel(TsgHandle* h, int num_sms, int* grid, bool* one_wave = nullptr) {
+  size_t smem = smem_bytes<P, W, E>() + extra_smem();
+  CK(cudaFuncSetAttribute(tb_env_kernel<P, MODE, W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<P, MODE, W>, W * 32, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb_env_kernel<P, MODE, W, E>, W * 32, smem));
   if (per_sm < 1) { g_err = "tsg_create: kernel does not fit on an SM"; return -1; }
   // what is not carved out for shared memory stays L1, which serves the spilled contacts and the lanes' local memory
-  int need = ((h->n_envs + EPW - 1) / EPW + W - 1) / W + ((h->n_pool + EPW - 1) / EPW + W - 1) / W;
+  int need = ((h->n_envs + E - 1) / E + W - 1) / W + ((h->n_pool + E - 1) / E + W - 1) / W;
   int full = num_sms * per_sm;
   *grid = need < full ? need : full;
-  if (MODE == MODE_STEP && (W == TB_WARPS) == (h->shape == 0)) {
-    cudaFuncAttributes a;
-    CK(cudaFuncGetAttributes(&a, tb_env_kernel<P, MODE, W>));
-    h->regs = a.numRegs; h->smem = smem;
-  }
+  if (one_wave) *one_wave = need <= full;
+  return 0;
+}
+template <typename P, int MODE, int W, int E = EPW>
+static int note_kernel(TsgHandle* h) {
+  cudaFuncAttributes a;
+  CK(cudaFuncGetAttributes(&a, tb_env_kernel<P, MODE, W, E>));
+  h->regs = a.numRegs; h->smem = smem_bytes<P, W, E>() + extra_smem(); h->warps = W; h->epw = E;
   return 0;
 }
 // CTA shape of the step kernel.  A batch that fits the machine at once in the small shape (2 CTAs of TB_WARPS_SMALL
 // warps per SM) is latency bound by a single round, which is shorter with fewer envs waiting for the slowest one at
 // the alignment barriers (4096 envs, steady state: 815k env-steps/s against 740k); larger batches run many rounds per
-// SM and the wide shape has the better throughput (131 072 envs: 1.40M against 1.20M).  profiles/r2_*.
-static int pick_shape(int n_envs, int num_sms) {
+// SM and the wide shape has the better throughput (131 072 envs: 1.40M against 1.20M).  Fewer envs per warp in the
+// small shape (TB_EPW_SMALL 5 or 4 with 3-4 warps) shorten a round only when the machine has room: +8 % at 2048 envs,
+// -7 to -14 % at 4096 (more warps per SM, each slower), so the default stays 10.  profiles/r2_ab_variants.log.
+static int shape_override() {
   const char* e = getenv("TSG_SHAPE");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
-  int rounds_small = ((n_envs + EPW - 1) / EPW + TB_WARPS_SMALL - 1) / TB_WARPS_SMALL;
-  return rounds_small <= 2 * num_sms ? 1 : 0;
+  return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1;
 }
 template <typename P>
 static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
@@ -274,9 +280,12 @@ static int setup_model(TsgHandle* h, const TsgModel* model, int sms) {
   if (!err.empty()) FAIL("tsg_create: " + err);
   CK(cudaMalloc(&h->d_model, sizeof(dm)));
   CK(cudaMemcpy(h->d_model, &dm, sizeof(dm), cudaMemcpyHostToDevice));
-  h->shape = pick_shape(h->n_envs, sms);
-  if (setup_kernel<P, MODE_STEP, TB_WARPS>(h, sms, &h->grid[MODE_STEP]) || setup_kernel<P, MODE_STEP, TB_WARPS_SMALL>(h, sms, &h->grid_small) ||
+  bool small_one_wave = false;
+  if (setup_kernel<P, MODE_STEP, TB_WARPS>(h, sms, &h->grid[MODE_STEP]) ||
+      setup_kernel<P, MODE_STEP, TB_WARPS_SMALL, TB_EPW_SMALL>(h, sms, &h->grid_small, &small_one_wave) ||
       setup_kernel<P, MODE_RESET, TB_WARPS>(h, sms, &h->grid[MODE_RESET]) || setup_kernel<P, MODE_FORWARD, TB_WARPS>(h, sms, &h->grid[MODE_FORWARD])) return -2;
+  h->shape = shape_override() >= 0 ? shape_override() : (small_one_wave ? 1 : 0);
+  if (h->shape == 1 ? note_kernel<P, MODE_STEP, TB_WARPS_SMALL, TB_EPW_SMALL>(h) : note_kernel<P, MODE_STEP, TB_WARPS>(h)) return -2;
   int gmax = h->grid[0] > h->grid[1] ? h->grid[0] : h->grid[1];
   if (h->grid[2] > gmax) gmax = h->grid[2];
   size_t slots = (size_t)gmax * TB_WARPS > (size_t)h->grid_small * TB_WARPS_SMALL ? (size_t)gmax * TB_WARPS : (size_t)h->grid_small * TB_WARPS_SMALL;
