@@ -82,6 +82,7 @@ struct EnvSh {
 #endif
   Con<sreal>* spill;      // global memory: 3 * KS slots of this env-in-flight
   int ncl[3];             // contacts owned by each lane
+  int ngl[3];             // ... of which the first ngl are ground contacts (world - own bar); bar-bar contacts follow
   int cpl[3];             // which blocks below the diagonal exist (set by the pair owners)
   int nact, overflow, bad, niter, nls, nmpr;
   sreal barforce;
@@ -402,47 +403,40 @@ template <typename real> TB_FN void blk_bwd(const real* L, real* x) {   // x <- 
     x[i] = t;
   }
 }
-// X <- X L^-T D^-1   (X a full 6x6 block below the diagonal block L D L^T), row by row
-template <typename real> TB_FN void blk_trsm(real* Xg, const real* Lg, const real* dinvg) {
-  real L[21], dinv[6];
+// Row-split forms of X <- X L^-T D^-1 and C -= A diag(d) B^T: the three lanes of an env share a block operation, two
+// rows each (r0 = 2 * bar), so the warp's instruction stream carries two rows instead of six.
+// rows r0, r0 + 1 of X <- X L^-T D^-1 ; L (packed, unit lower) and dinv in registers
+template <typename real> TB_FN void blk_trsm_rows2(real* Xg, const real* L, const real* dinv, int r0) {
   TB_UNROLL
-  for (int e = 0; e < 21; e++) L[e] = Lg[e];
-  TB_UNROLL
-  for (int e = 0; e < 6; e++) dinv[e] = dinvg[e];
-  TB_UNROLL1
-  for (int r = 0; r < 6; r++) {
+  for (int rr = 0; rr < 2; rr++) {
+    real* X = Xg + 6 * (r0 + rr);
     real u[6];
     TB_UNROLL
     for (int k = 0; k < 6; k++) {
-      real t = Xg[6 * r + k];
+      real t = X[k];
       TB_UNROLL
       for (int q = 0; q < k; q++) t -= u[q] * L[k * (k + 1) / 2 + q];
       u[k] = t;
     }
     TB_UNROLL
-    for (int k = 0; k < 6; k++) Xg[6 * r + k] = u[k] * dinv[k];
+    for (int k = 0; k < 6; k++) X[k] = u[k] * dinv[k];
   }
 }
-// C -= A diag(d) B^T, d = diagonal of the packed block Ld.  sym: C packed lower (A == B), else C full row-major.
-template <typename real> TB_FN void blk_mulsub(real* Cg, const real* Ag, const real* Ldg, const real* Bg, bool sym) {
-  real Bm[36], d[6];
+// rows r0, r0 + 1 of C -= A diag(d) B^T ; B (full 6x6) and d in registers.  sym: C packed lower (entries j <= i only)
+template <typename real> TB_FN void blk_mulsub_rows2(real* Cg, const real* Ag, const real* d, const real* Bm, bool sym, int r0) {
   TB_UNROLL
-  for (int e = 0; e < 36; e++) Bm[e] = Bg[e];
-  TB_UNROLL
-  for (int k = 0; k < 6; k++) d[k] = Ldg[k * (k + 1) / 2 + k];
-  TB_UNROLL1
-  for (int i = 0; i < 6; i++) {
+  for (int rr = 0; rr < 2; rr++) {
+    const int i = r0 + rr;
     real ad[6];
     TB_UNROLL
     for (int k = 0; k < 6; k++) ad[k] = Ag[6 * i + k] * d[k];
     real* Crow = sym ? Cg + i * (i + 1) / 2 : Cg + 6 * i;
     TB_UNROLL
     for (int j = 0; j < 6; j++) {
-      if (sym && j > i) break;
       real sacc = 0;
       TB_UNROLL
       for (int k = 0; k < 6; k++) sacc += ad[k] * Bm[6 * j + k];
-      Crow[j] -= sacc;
+      if (!sym || j <= i) Crow[j] -= sacc;
     }
   }
 }
@@ -816,6 +810,7 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       }
     }
   }
+  const int ngr = nmine;   // ground contacts come first in the lane's list
   // bar-bar: this lane takes pair p = its bar index: (0,1), (0,2), (1,2).  All geoms lie on their bar's axis, so the 25
   // geom pairs are filtered with scalars: MuJoCo's bounding-sphere test, then an analytic capsule bound (conservative:
   // MPR reports penetration only for intersecting shapes).  Sphere-sphere pairs are analytic; the others are listed in
@@ -898,7 +893,7 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       }
     }
   }
-  if (pass_on) S.ncl[b] = nmine;
+  if (pass_on) { S.ncl[b] = nmine; S.ngl[b] = ngr; }
   wsync();
   // rows of this lane's contacts: velocity, impedance, reference acceleration, residual at qacc_smooth
   sreal csm = 0;
@@ -979,8 +974,17 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
     sreal gn = 0;
     if (act) {
       sreal Fw[3] = {0, 0, 0}, Tw[3] = {0, 0, 0};
+      // own ground contacts (every lane on its own list: full lanes), then the bar-bar contacts of all three owners
       TB_UNROLL1
-      for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
+      for (int s = 0; s < ngr; s++) {
+        const Con<sreal>& c = con_of(S, b, s);
+        if (c.zone == ZONE_TOP) continue;
+        sreal t[3];
+        cross3(t, c.r2, c.wr);
+        for (int k = 0; k < 3; k++) { Fw[k] += c.wr[k]; Tw[k] += t[k] + c.wr[3 + k]; }
+      }
+      TB_UNROLL1
+      for (int o = 0; o < 3; o++) for (int s = S.ngl[o]; s < S.ncl[o]; s++) {
         const Con<sreal>& c = con_of(S, o, s);
         if (c.zone == ZONE_TOP) continue;
         sreal t[3];
@@ -1015,7 +1019,13 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       H[9] = Iw[0]; H[13] = Iw[1]; H[14] = Iw[2]; H[18] = Iw[3]; H[19] = Iw[4]; H[20] = Iw[5];
       S.cpl[b] = 0;
       TB_UNROLL1
-      for (int o = 0; o < 3; o++) for (int s = 0; s < S.ncl[o]; s++) {
+      for (int s = 0; s < ngr; s++) {   // own ground contacts
+        const Con<sreal>& c = con_of(S, b, s);
+        if (c.zone == ZONE_TOP) continue;
+        side_hessian(c, m, c.r2, H);
+      }
+      TB_UNROLL1
+      for (int o = 0; o < 3; o++) for (int s = S.ngl[o]; s < S.ncl[o]; s++) {   // bar-bar contacts of all owners
         const Con<sreal>& c = con_of(S, o, s);
         if (c.zone == ZONE_TOP) continue;
         if (c.b2 != b && c.b1 != b) continue;
@@ -1028,9 +1038,9 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
         for (int e = 0; e < 36; e++) X[e] = 0;
         bool anyx = false;
         TB_UNROLL1
-        for (int s = 0; s < nmine; s++) {
+        for (int s = ngr; s < nmine; s++) {
           const Con<sreal>& c = con_of(S, b, s);
-          if (c.b1 < 0 || c.zone == ZONE_TOP) continue;
+          if (c.zone == ZONE_TOP) continue;
           if (c.b2 > c.b1) cross_hessian(c, m, c.r2, c.r1, X); else cross_hessian(c, m, c.r1, c.r2, X);
           anyx = true;
         }
@@ -1053,12 +1063,33 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
       if (uni_any(go && (c10 || c20 || c21), aligned && TB_ALIGN_LEVEL >= 3)) {
         if (go && b == 0 && !alone) for (int k = 0; k < 6; k++) xs[k] = x[k];   // z0
         wsync();
-        if ((b == 1 && c10) || (b == 2 && c20)) blk_trsm(O[b - 1], D[0], dinv);
+        // column 0: the off-diagonal blocks O10, O20 and the updates they cause, two rows per lane
+        if (c10 || c20) {
+          sreal Lr[21], dv[6];
+          TB_UNROLL
+          for (int e = 0; e < 21; e++) Lr[e] = D[0][e];
+          TB_UNROLL
+          for (int e = 0; e < 6; e++) dv[e] = dinv[e];
+          if (c10) blk_trsm_rows2(O[0], Lr, dv, 2 * b);
+          if (c20) blk_trsm_rows2(O[1], Lr, dv, 2 * b);
+        }
+        if (f21 && !c21in) for (int e = 0; e < 12; e++) O[2][12 * b + e] = 0;
         wsync();
-        if ((b == 1 && c10) || (b == 2 && c20)) blk_mulsub(D[b], O[b - 1], D[0], O[b - 1], true);
-        if (b == 0 && f21) {
-          if (!c21in) for (int e = 0; e < 36; e++) O[2][e] = 0;
-          blk_mulsub(O[2], O[1], D[0], O[0], false);
+        if (c10 || c20) {
+          sreal d0[6], Bm[36];
+          TB_UNROLL
+          for (int k = 0; k < 6; k++) d0[k] = D[0][k * (k + 1) / 2 + k];
+          if (c10) {
+            TB_UNROLL
+            for (int e = 0; e < 36; e++) Bm[e] = O[0][e];
+            blk_mulsub_rows2(D[1], O[0], d0, Bm, true, 2 * b);
+            if (f21) blk_mulsub_rows2(O[2], O[1], d0, Bm, false, 2 * b);
+          }
+          if (c20) {
+            TB_UNROLL
+            for (int e = 0; e < 36; e++) Bm[e] = O[1][e];
+            blk_mulsub_rows2(D[2], O[1], d0, Bm, true, 2 * b);
+          }
         }
         wsync();
         if (b == 1 && c10) {
@@ -1068,8 +1099,26 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
         }
         if (go && b == 1 && !alone) for (int k = 0; k < 6; k++) xs[6 + k] = x[k];   // z1
         wsync();
+        // column 1: O21 and its update of D2, two rows per lane
+        if (c21) {
+          sreal Lr[21], dv[6];
+          TB_UNROLL
+          for (int e = 0; e < 21; e++) Lr[e] = D[1][e];
+          TB_UNROLL
+          for (int e = 0; e < 6; e++) dv[e] = dinv[6 + e];
+          blk_trsm_rows2(O[2], Lr, dv, 2 * b);
+        }
+        wsync();
+        if (c21) {
+          sreal d1[6], Bm[36];
+          TB_UNROLL
+          for (int k = 0; k < 6; k++) d1[k] = D[1][k * (k + 1) / 2 + k];
+          TB_UNROLL
+          for (int e = 0; e < 36; e++) Bm[e] = O[2][e];
+          blk_mulsub_rows2(D[2], O[2], d1, Bm, true, 2 * b);
+        }
+        wsync();
         if (b == 2 && (c20 || c21)) {
-          if (c21) { blk_trsm(O[2], D[1], dinv + 6); blk_mulsub(D[2], O[2], D[1], O[2], true); }
           blk_ldl(D[2], dinv + 12);
           if (c20) blk_gemv_sub(x, O[1], xs);
           if (c21) blk_gemv_sub(x, O[2], xs + 6);

@@ -198,6 +198,40 @@ def test_many_contacts_per_bar(oracle, yaw, dx, ncon0, nstep):
         assert np.abs(em.warm - mj.qacc_warmstart).max() <= 1e-9 * np.abs(mj.qacc_warmstart).max()
 
 
+def _lying_bar(x, y, z, yaw):
+    """pose of a bar lying flat (axis horizontal), its axis turned by yaw about z"""
+    lay = [np.cos(np.pi / 4), np.sin(np.pi / 4), 0, 0]
+    return [x, y, z] + _quat_mul([np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)], lay)
+
+
+@pytest.mark.parametrize("scene", ["triangle", "two_on_one"])
+def test_coupled_bars_block_factorisation(oracle, scene):
+    """bars lying across one another: the Hessian blocks between bars exist, so the distributed block LDL^T runs its
+    coupled stages.  triangle: every pair touches (all three blocks below the diagonal); two_on_one: bars 1 and 2 both
+    cross bar 0 but not each other (blocks (1,0), (2,0) present, (2,1) appears as fill-in only)."""
+    if scene == "triangle":
+        q = []
+        for b in range(3):
+            phi = np.pi / 2 + 2 * np.pi / 3 * b
+            q += _lying_bar(0.08 * np.cos(phi), 0.08 * np.sin(phi), 0.0375 + 0.02 * b, phi)
+        want = {(0, 1), (0, 2), (1, 2)}
+    else:
+        q = _lying_bar(0, 0, 0.0375, np.pi / 2) + _lying_bar(-0.15, 0, 0.09, 0.0) + _lying_bar(0.15, 0, 0.09, 0.05)
+        want = {(0, 1), (0, 2)}
+    mj, em = oracle.MjLike("flat"), E.Emul("flat")
+    mj.reset_data(); mj.qpos[:] = q; mj.ctrl[:] = -0.2
+    for st in range(4):
+        em.rec[0:21] = mj.qpos; em.rec[21:39] = mj.qvel; em.rec[39:57] = mj.qacc_warmstart
+        mj.step(1)
+        ten, cfrc, stats = em.mj_step(np.full(6, -0.2), 1)
+        pairs = {((c.geom1 - 1) // 5, (c.geom2 - 1) // 5) for c in mj.contacts() if not c.exclude and c.dist < 0 and c.geom1 > 0}
+        if st == 0:
+            assert pairs == want
+        assert stats[0] == mj.nefc // 6 and stats[4] == 0
+        assert np.abs(em.qvel - mj.qvel).max() < 1e-10
+        assert np.abs(em.warm - mj.qacc_warmstart).max() <= 1e-9 * np.abs(mj.qacc_warmstart).max()
+
+
 @pytest.mark.parametrize("task", ["straight", "tracking", "aiming", "vel_track"])
 def test_obs_noise_parity(task):
     """use_obs_noise (tr_env.py:142, 552-644): the CUDA source's noisy observation against the oracle's restatement on
