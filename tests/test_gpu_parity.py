@@ -208,6 +208,61 @@ def test_state_round_trip_and_f32_ctrl():
     v.close()
 
 
+@pytest.mark.parametrize("env,task", [("tensegrity_env", "turn"), ("tr_env", "aiming")])
+def test_checkpoint_restore_includes_the_heading_ring(env, task):
+    """records + heading ring saved from one handle and restored into a fresh one continue bit for bit on the tasks
+    whose reward reads the delayed heading (legacy turn: 25-slot ring, tensegrity_env.py:242,326-345)."""
+    import torch
+    n = 32
+    v = _vec(n, "flat", env, desired_action=task, auto_reset=False, terminate_when_unhealthy=False)
+    v.reset_tensor()
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    acts = -0.45 + 0.3 * torch.rand(40, n, 6, generator=g, device="cuda", dtype=torch.float64)
+    for k in range(30):                       # fill the ring past its length
+        v.step_tensor(acts[k])
+    rec, hd = v.get_records(), v.get_heading()
+    ref = [tuple(t.clone() for t in v.step_tensor(acts[30 + k])) for k in range(10)]
+    w = _vec(n, "flat", env, desired_action=task, auto_reset=False, terminate_when_unhealthy=False)
+    w.set_records(rec); w.set_heading(hd)
+    for k in range(10):
+        obs, rew, done = w.step_tensor(acts[30 + k])
+        assert torch.equal(obs, ref[k][0]) and torch.equal(rew, ref[k][1]) and torch.equal(done, ref[k][2])
+    # without the ring the delayed-heading reward differs
+    u = _vec(n, "flat", env, desired_action=task, auto_reset=False, terminate_when_unhealthy=False)
+    u.set_records(rec)
+    _, rew_u, _ = u.step_tensor(acts[30])
+    if task == "turn":
+        assert not torch.equal(rew_u, ref[0][1])
+    for e in (v, w, u):
+        e.close()
+
+
+def test_pooled_reset_keeps_the_true_observation_with_obs_noise():
+    """use_obs_noise + reset pool: an env that is handed a pool slot gets the slot's noise-free reset observation in
+    real_obs (tr_env.py:505 `real_observation`), not the previous episode's last one."""
+    import torch
+    n = 256
+    v = _vec(n, "flat", "tr_env", desired_action="straight", auto_reset=True, reset_pool=128, use_obs_noise=True,
+             max_episode_steps=60)
+    v.reset_tensor()
+    a = torch.full((n, 6), -0.2, device="cuda", dtype=torch.float64)
+    for _ in range(58):                       # the pool slots finish their 50 warm-up steps meanwhile
+        v.step_tensor(a)
+    before = v.real_obs.clone()
+    obs, rew, done = None, None, torch.zeros(n, dtype=torch.bool, device="cuda")
+    while not bool(done.any()):
+        before = v.real_obs.clone()
+        obs, rew, done = v.step_tensor(a)
+    d = done.bool()
+    assert v.pool_stats()["assigned"] > 0                      # slots were handed out
+    real = v.real_obs
+    diff = (obs - real).abs().amax(1)
+    assert bool((diff[d] > 0).all()) and bool((diff[d] < 1.0).all())            # noisy obs = true reset obs + noise
+    # a fresh reset pose (bars re-posed from the pose table) is not the collapsed pose of the finished episode
+    assert bool(((real - before).abs().amax(1)[d] > 1e-3).all())
+    v.close()
+
+
 @pytest.mark.parametrize("xml,n", [("flat", 65536), ("uneven", 16384)])
 def test_properties_at_scale(xml, n):
     """size-independent invariants at bench-scale batch sizes."""
