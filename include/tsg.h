@@ -90,7 +90,8 @@ int tsg_destroy(TsgHandle *h);
 int tsg_num_envs(const TsgHandle *h);
 int tsg_obs_dim(const TsgHandle *h);
 int tsg_launches(const TsgHandle *h); /* kernels launched so far by this handle */
-/* dynamic shared memory per CTA and warps per CTA of the step kernel (for occupancy reports) */
+/* step-kernel launch shape of this handle (for occupancy reports): *warps_per_cta = warps per CTA * 100 + lanes per
+ * env (503 = 5 warps, 3 lanes per env), dynamic shared memory per CTA, registers per thread */
 int tsg_kernel_config(const TsgHandle *h, int *warps_per_cta, int *smem_bytes, int *regs_per_thread);
 
 /* reset the envs whose mask byte is non-zero (mask_dev NULL = all).  draws_in_dev: optional

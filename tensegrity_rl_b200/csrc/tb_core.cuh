@@ -725,16 +725,21 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
     }
   }
   if (m.floor_type != 0) {
-    // height field (frame axis-aligned at fpos): per geom, the prisms under its AABB whose top reaches the AABB's
-    // bottom (MuJoCo's test) and that the geom can reach (conservative cull) are listed in a bit mask; the lanes of
-    // the warp then take their candidates through MPR round by round, together
+    // height field (frame axis-aligned at fpos).  Pass 1: per geom, the prisms under its AABB whose top reaches the
+    // AABB's bottom (MuJoCo's test) and that the geom can reach (conservative cull) are listed in a bit mask, kept with
+    // the geom's cell window in the env's solver scratch (idle until the Newton stage, behind the lanes' MPR objects).
+    // Pass 2: the lanes of the warp take their candidates through MPR round by round, together, each lane walking its
+    // own geoms in order -- the number of rounds is the largest candidate count of a LANE, not the sum over the five
+    // geoms of the largest count per geom, and the contacts are found in the same order.
+    int* hfc = reinterpret_cast<int*>(&S.u.sol.D[0][0]) + 240 + 20 * b;   // [geom][mask, cmin, rmin, per_row]
+    static_assert(6 * sizeof(CObj<sreal>) <= 960 && (240 + 60) * sizeof(int) <= sizeof(S.u.sol.D) + sizeof(S.u.sol.O), "solver scratch too small");
     TB_UNROLL1
     for (int g = 0; g < 5; g++) {
       const int Gi = 5 * b + g;
       unsigned cand = 0;
       int cmin = 0, rmin = 0, per_row = 1;
-      real gc[3], pos[3];
-      for (int k = 0; k < 3; k++) { gc[k] = B.x[k] + R[3 * k + 2] * m.gz[Gi]; pos[k] = gc[k] - m.fpos[k]; }
+      real pos[3];
+      for (int k = 0; k < 3; k++) pos[k] = B.x[k] + R[3 * k + 2] * m.gz[Gi] - m.fpos[k];
       const real r = m.gsize[Gi][0], hl = m.gsize[Gi][1], rb = m.gbound[Gi];
       if (pass_on) {
         bool ok = true;
@@ -771,16 +776,25 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
             }
           } else per_row = 1;
         }
+        hfc[4 * g] = (int)cand; hfc[4 * g + 1] = cmin; hfc[4 * g + 2] = rmin; hfc[4 * g + 3] = per_row;
       }
+    }
+    {
+      int g = -1, cmin = 0, rmin = 0, per_row = 1;
+      unsigned cand = 0;
       TB_UNROLL1
-      while (any(cand != 0)) {
-        const bool has = cand != 0;
+      for (;;) {
+        if (pass_on) while (cand == 0 && g < 4) { g++; cand = (unsigned)hfc[4 * g]; cmin = hfc[4 * g + 1]; rmin = hfc[4 * g + 2]; per_row = hfc[4 * g + 3]; }
+        const bool has = pass_on && cand != 0;
+        if (!any(has)) break;
         // the narrow phase runs in the solver's precision: MPR's 1e-6 tolerance is out of fp32's reach.  The lane's two
-        // objects live in the env's solver scratch (unused until the Newton stage), not in per-thread local memory; only
-        // lanes with a candidate write them (the idle lanes 30, 31 alias the last env's slice)
+        // objects live in the env's solver scratch, not in per-thread local memory; only lanes with a candidate write
+        // them (the idle lanes 30, 31 alias the last env's slice)
         CObj<sreal>* objs = reinterpret_cast<CObj<sreal>*>(&S.u.sol.D[0][0]) + 2 * b;
         CObj<sreal>&o1 = objs[0], &o2 = objs[1];
+        real gc[3] = {0, 0, 0};
         if (has) {
+          const int Gi = 5 * b + g;
           const int q = lowbit(cand);
           cand &= cand - 1;
           CObj<real> pr;
@@ -788,8 +802,8 @@ TB_FN void phys(BarState<P>& B, EnvSh<P>& S, const ModelT<typename P::real>& m, 
           o1.type = 100;
           for (int k = 0; k < 3; k++) { o1.px[k] = pr.px[k]; o1.py[k] = pr.py[k]; o1.pz[k] = pr.pz[k]; }
           o1.pbase = pr.pbase;
-          o2.type = m.gtype[Gi]; o2.size[0] = r; o2.size[1] = hl;
-          for (int k = 0; k < 3; k++) o2.pos[k] = pos[k];
+          o2.type = m.gtype[Gi]; o2.size[0] = m.gsize[Gi][0]; o2.size[1] = m.gsize[Gi][1];
+          for (int k = 0; k < 3; k++) { gc[k] = B.x[k] + R[3 * k + 2] * m.gz[Gi]; o2.pos[k] = gc[k] - m.fpos[k]; }
           for (int k = 0; k < 3; k++) o2.axis[k] = R[3 * k + 2];
           nmpr++;
         }

@@ -227,7 +227,9 @@ class TensegrityVecEnv:
     def kernel_config(self):
         w, s, r = C.c_int(), C.c_int(), C.c_int()
         _lib.check(self.L.tsg_kernel_config(self.h, C.byref(w), C.byref(s), C.byref(r)))
-        return {"warps_per_cta": w.value, "smem_bytes_per_cta": s.value, "regs_per_thread": r.value}
+        # the C ABI packs (warps per CTA, lanes per env) into one int: w * 100 + lanes
+        return {"warps_per_cta": w.value // 100, "lanes_per_env": w.value % 100, "envs_per_warp": 10,
+                "smem_bytes_per_cta": s.value, "regs_per_thread": r.value}
 
     # SB3 VecEnv odds and ends
     def close(self):

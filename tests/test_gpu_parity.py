@@ -481,7 +481,7 @@ def test_ragged_batches_give_identical_envs():
 
     def run(n):
         v = TensegrityVecEnv(n, xml_file="flat", env="tr_env", seed=11, auto_reset=False)
-        assert v.kernel_config()["warps_per_cta"] % 100 == 3   # lanes per env
+        assert v.kernel_config()["lanes_per_env"] == 3
         v.reset_tensor()
         ids = torch.arange(n, device="cuda", dtype=torch.float64)
         for st in range(2):
