@@ -392,7 +392,7 @@ def main():
                          "flop_model": "SURVEY 8(d): 20 x [3.0k + 0.45k ncon + n_iter (1.5k + 0.9k ncon)], FMA = 2, with the measured means",
                          "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                  "algorithmic_bytes_per_env_step": balg, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                         "note": "latency bound: 5 resident warps per SM (shared memory: 3.6 KB per env, ten envs per warp) walking "
+                         "note": "latency bound: 6 resident warps per SM (shared memory: 3.6 KB per env, ten envs per warp) walking "
                                  "dependent fp64 chains in lock step; no pipe is above 15 % busy (profiles/r2_*)"},
         }
         if e2e:
