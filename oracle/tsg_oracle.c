@@ -1,8 +1,11 @@
 /* tsg_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, not product code).  See tsg_oracle.h.
  *
  * Readable dense fp64 restatement of MuJoCo 2.3.7's mj_step for the 3-bar
- * tensegrity.  PARITY UNPINNED (no MuJoCo binary, no
- * reference golden vectors).  Section comments name the MuJoCo stage restated.
+ * tensegrity.  PARITY UNPINNED at the level of single-step
+ * dynamics (no MuJoCo binary, no stored trajectory in the reference); kinematics,
+ * tendon lengths and the observation layout are pinned to 1e-12 against the
+ * `_last_obs` vectors stored in the reference's checkpoints
+ * (tests/test_golden_last_obs.py).  Section comments name the MuJoCo stage restated.
  */
 #include "tsg_oracle.h"
 
