@@ -623,24 +623,45 @@ def test_golden_last_obs_through_the_cuda_path():
 
 
 @pytest.mark.gpu
-def test_tracking_checkpoint_rollout_is_reported():
-    """models_traj/SAC_16525000_track.zip (tr_env `tracking`, the heading-reward path of BASELINE configs[3],
-    tr_env.py:425-459): its ep_info_buffer holds return 224 over 253 steps = 0.885 per step at training time.  This
-    simulator does NOT reproduce that figure (measured 0.15 per step on the uneven XML's bar geometry over a flat floor,
-    episode length 299 against 253): unlike the four legacy checkpoints, whose training statistics are reproduced within
-    5 %, the training configuration of this one (model file, waypoint range, reward amplitudes) is not recoverable from
-    the repository.  The test reports the numbers and asserts only that the policy makes progress towards its waypoints
-    (positive return per step) without tripping any solver safeguard."""
+@pytest.mark.parametrize("policy,task,dirn", [("traj_track", "tracking", 1), ("traj_ccw", "turn", 1), ("traj_cw", "turn", -1)])
+def test_tr_env_checkpoint_rollouts_are_reported(policy, task, dirn):
+    """The 48-dim tr_env checkpoints (models_traj/SAC_16525000_track.zip, SAC_2175000_ccw.zip, SAC_1250000_cw.zip; the
+    heading-reward paths of BASELINE configs[3], tr_env.py:425-459) store their last 100 training episodes
+    (`ep_info_buffer`): 0.886 / 0.214 / 0.212 return per step.  The ccw / cw checkpoints were trained with the three
+    waypoint slots of the observation at zero (their `_last_obs` holds zeros there, and run.py test3 :262-272 blanks
+    them), i.e. on a turning reward: they are run on `desired_action="turn"` with those slots zeroed.  This simulator
+    does NOT reproduce these figures (measured: tracking 0.15 per step, episode length 299 against 253; ccw / cw 0.15 /
+    0.13 against 0.21, episode length ~200 against 681 / 3673): unlike the four legacy checkpoints, whose training
+    statistics are reproduced within 5 %, the training configuration of these (model file, waypoint range, reward
+    amplitudes, termination rule) is not recoverable from the repository.  The test prints ours beside the reference's
+    and asserts that the rollouts run without tripping any solver safeguard and that each policy earns a positive
+    return per step on its task (it walks towards its waypoints / turns the way it was trained to)."""
     import json, os
+    import torch
     from tensegrity_rl_b200 import SacActor
-    from tensegrity_rl_b200.rollout import rollout
     G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "last_obs.json")))
-    ref = G["traj_track"]["ep_return_mean"] / G["traj_track"]["ep_len_mean"]
-    v = _vec(2048, "legacy_flat", "tr_env", desired_action="tracking", auto_reset=True, reset_pool=512)
+    ref = G[policy]["ep_return_mean"] / G[policy]["ep_len_mean"]
+    n = 2048
+    v = _vec(n, "legacy_flat", "tr_env", desired_action=task, desired_direction=dirn, auto_reset=True, reset_pool=512)
     v.reset_tensor()
-    s = rollout(v, SacActor("traj_track"), 600)
-    got, length = s["return_sum"] / s["length_sum"], s["length_sum"] / max(1.0, s["episodes"])
-    print("track: return/step ours %.3f reference %.3f | episode length ours %.0f reference %.0f"
-          % (got, ref, length, G["traj_track"]["ep_len_mean"]))
-    assert got > 0.05 and int(v.info[:, 28].sum()) == 0 and int(v.info[:, 29].sum()) == 0
+    actor = SacActor(policy)
+    ret_sum = len_sum = 0.0
+    episodes = 0
+    ret = torch.zeros(n, device="cuda", dtype=torch.float64)
+    ln = torch.zeros(n, device="cuda", dtype=torch.float64)
+    for _ in range(600):
+        o = torch.zeros(n, 48, device="cuda", dtype=torch.float32)
+        o[:, :v.obs_dim] = v.obs32                              # tracking: all 48 slots; turn: 45 + zeros
+        obs, rew, done = v.step_tensor(actor(o, False).double())
+        ret += rew; ln += 1
+        d = done.bool()
+        ret_sum += float(ret[d].sum()); len_sum += float(ln[d].sum()); episodes += int(d.sum())
+        ret[d] = 0; ln[d] = 0
+    length = len_sum / max(1, episodes)                         # finished episodes only
+    ret_sum += float(ret.sum()); len_sum += float(ln.sum())
+    got = ret_sum / len_sum
+    print("%s: return/step ours %.3f reference %.3f | episode length ours %.0f reference %.0f"
+          % (policy, got, ref, length, G[policy]["ep_len_mean"]))
+    assert int(v.info[:, 28].sum()) == 0 and int(v.info[:, 29].sum()) == 0
+    assert got > 0.05
     v.close()
