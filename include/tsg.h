@@ -71,7 +71,9 @@ const char *tsg_last_error(void);
 int tsg_version(void);
 int tsg_device_count(void);
 
-/* n_envs independent envs on CUDA device `device`; env_id_base offsets the RNG stream ids (rank sharding) */
+/* n_envs independent envs on CUDA device `device`; env_id_base offsets the RNG stream ids (rank sharding).
+ * Replaces MujocoEnv.__init__ -> MjModel.from_xml_path + MjData (tr_env.py:274-276, tensegrity_env.py:239-241) and the
+ * env constructor's bookkeeping (tr_env.py:130-285). */
 int tsg_create(const TsgModel *model, const TsgEnvConfig *cfg, int n_envs, int device, long long env_id_base,
                TsgHandle **out);
 /* same, with n_pool background reset slots: every tsg_step(auto_reset=1) launch also advances each not-yet-ready
@@ -91,17 +93,21 @@ int tsg_num_envs(const TsgHandle *h);
 int tsg_obs_dim(const TsgHandle *h);
 int tsg_launches(const TsgHandle *h); /* kernels launched so far by this handle */
 /* step-kernel launch shape of this handle (for occupancy reports): *warps_per_cta = warps per CTA * 100 + lanes per
- * env (503 = 5 warps, 3 lanes per env), dynamic shared memory per CTA, registers per thread */
+ * env (603 = 6 warps, 3 lanes per env), dynamic shared memory per CTA, registers per thread */
 int tsg_kernel_config(const TsgHandle *h, int *warps_per_cta, int *smem_bytes, int *regs_per_thread);
 
-/* reset the envs whose mask byte is non-zero (mask_dev NULL = all).  draws_in_dev: optional
+/* Replaces env.reset(): MujocoEnv.reset -> reset_model (tr_env.py:709-872, tensegrity_env.py:433-512; run.py:119).
+ * reset the envs whose mask byte is non-zero (mask_dev NULL = all).  draws_in_dev: optional
  * [n_envs][TSG_NDRAW] explicit random draws (tests); otherwise Philox(seed, env id, reset count).
  * obs_dev / obs32_dev (optional) receive the reset observation rows of the reset envs;
  * term_obs_dev (optional) first receives a copy of obs_dev rows about to be overwritten. */
 int tsg_reset(TsgHandle *h, const uint8_t *mask_dev, unsigned long long seed, const double *draws_in_dev,
               double *obs_dev, float *obs32_dev, double *term_obs_dev, void *stream);
 
-/* one env step for all envs.  ctrl_dev: [n_envs][6] (f64 or f32 per ctrl_dtype).  Optional outputs:
+/* Replaces env.step(action): tr_env.step (tr_env.py:327-527) / tensegrity_env.step (tensegrity_env.py:291-410),
+ * i.e. do_simulation -> mujoco.mj_step(nstep = frame_skip) + mj_rnePostConstraint, _get_obs, reward, termination
+ * (run.py:138).  info columns = the reference's info dict keys (TSG_INFO_*; tr_env.py:496-512).
+ * one env step for all envs.  ctrl_dev: [n_envs][6] (f64 or f32 per ctrl_dtype).  Optional outputs:
  * obs_dev [n][obs_dim] f64, obs32_dev f32 copy, reward_dev [n] f64, done_dev [n] u8
  * (terminated|truncated), info_dev [n][TSG_INFO_DIM] f64.  If auto_reset != 0 the envs that are done
  * are reset in the same call (their obs rows then hold the first observation of the new episode
@@ -120,14 +126,16 @@ int tsg_set_real_obs(TsgHandle *h, double *real_obs_dev);
 /* the noise-free observations of the last step / reset, HOST buffer [n_envs][obs_dim] (synchronous) */
 int tsg_get_real_obs_host(TsgHandle *h, double *real_obs);
 
-/* mj_forward on the stored states: refreshes the kinematics-derived bookkeeping, optional obs/info */
+/* mj_forward on the stored states (MujocoEnv.set_state -> mujoco.mj_forward; tr_env.py:744,763,800):
+ * refreshes the kinematics-derived bookkeeping, optional obs/info */
 int tsg_forward(TsgHandle *h, double *obs_dev, double *info_dev, void *stream);
 
 /* same from host code (MujocoEnv.set_state of a single env): runs on the handle's own stream -- ordered with
  * tsg_step_host / tsg_reset_host -- and returns after the optional HOST obs / info rows are written */
 int tsg_forward_host(TsgHandle *h, double *obs, double *info);
 
-/* raw state access (HOST buffers, synchronous): any pointer may be NULL */
+/* raw state access (HOST buffers, synchronous): any pointer may be NULL.  Replaces reads / writes of data.qpos,
+ * data.qvel, data.act, data.qacc_warmstart, data.ctrl (tr_env.py:345,583; MujocoEnv.set_state) */
 int tsg_get_state_host(TsgHandle *h, double *qpos, double *qvel, double *act, double *qacc_warmstart, double *ctrl);
 int tsg_set_state_host(TsgHandle *h, const double *qpos, const double *qvel, const double *act,
                        const double *qacc_warmstart, const double *ctrl);
@@ -141,7 +149,8 @@ int tsg_set_heading_host(TsgHandle *h, const double *heading);
 /* last reset draws [n_envs][TSG_NDRAW], HOST buffer */
 int tsg_get_draws_host(TsgHandle *h, double *draws);
 
-/* convenience for host callers (the reference-facing Python plugin): host buffers in, host buffers out,
+/* the calls behind the reference-shaped single env (envs.py tr_env / tensegrity_env: run.py:119,138): host buffers
+ * in, host buffers out,
  * H2D/D2H copies on the handle's stream, synchronous. */
 int tsg_step_host(TsgHandle *h, const double *ctrl, double *obs, double *reward, uint8_t *done, double *info,
                   int auto_reset, unsigned long long seed, double *term_obs);
