@@ -286,6 +286,13 @@ def main():
             m2, _, _ = timed_run(e2, s, 10, 3, True)
             sweep[str(s)] = s * 10 / (m2 * 1e-3)
             e2.close()
+            if s <= 8192:   # BASELINE configs[1] proper: random ctrl, no resets inside the run (no pool slots to warm up)
+                e2 = TensegrityVecEnv(s, xml_file="flat", env="tr_env", device=local_rank, seed=0, auto_reset=False, reset_pool=0)
+                e2.reset_tensor()
+                settle(e2, s, 100, 555)
+                m2, _, _ = timed_run(e2, s, 10, 3, True)
+                sweep["%d_no_auto_reset" % s] = s * 10 / (m2 * 1e-3)
+                e2.close()
         # optional fp32 mode (north_star: 1e-4 tolerance class; the headline stays f64)
         try:
             e2 = TensegrityVecEnv(n, xml_file="flat", env="tr_env", device=local_rank, seed=0, auto_reset=True, reset_pool="auto", precision="f32")
